@@ -1,0 +1,418 @@
+/*
+ * oracle.c — scalar-float C restatement of the CLSuperPathTracer device code.
+ * TEST INFRASTRUCTURE ONLY — see oracle.h for who may use it and how it is pinned.
+ *
+ * Every function cites the reference lines it follows (paths relative to /root/reference).
+ * "base"  = CLSuperPathTracer/pathtracer.ocl
+ * "lmem"  = CLSuperPathTracer_lmem/pathtracer.ocl
+ * "nodof" = CLSuperPathTracer_lmem_NoDoF/pathtracer.ocl
+ * "grid"  = CLSuperPathTracer_trianglegrid/pathtracer.ocl
+ */
+#include "oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#ifndef PT_CONTRACT
+#define PT_CONTRACT 0
+#endif
+
+/* ------------------------------------------------------------ arithmetic policy */
+#if PT_CONTRACT
+static inline float MADD(float a, float b, float c) { return fmaf(a, b, c); } /* a*b + c, one rounding */
+static inline float MSUB(float a, float b, float c, float d) { return fmaf(a, b, -(c * d)); } /* a*b - c*d */
+static inline float POW4(float x) { float x2 = x * x; return x2 * x2; }
+#else
+static inline float MADD(float a, float b, float c) { return a * b + c; }
+static inline float MSUB(float a, float b, float c, float d) { return a * b - c * d; }
+static inline float POW4(float x) { return powf(x, 4.0f); }
+#endif
+
+int oracle_contract_mode(void) { return PT_CONTRACT; }
+
+typedef struct { float x, y, z; } V3;
+
+static inline V3 v3(float x, float y, float z) { V3 r = {x, y, z}; return r; }
+static inline V3 vsub(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+static inline V3 vscale(V3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
+/* a*s + b per component */
+static inline V3 vmadd(V3 a, float s, V3 b) { return v3(MADD(a.x, s, b.x), MADD(a.y, s, b.y), MADD(a.z, s, b.z)); }
+/* dot(): x,y,z summed left to right (w lanes are 0 in the reference) */
+static inline float dot3(V3 a, V3 b) { return MADD(a.z, b.z, MADD(a.y, b.y, a.x * b.x)); }
+static inline V3 cross3(V3 a, V3 b) {
+    return v3(MSUB(a.y, b.z, a.z, b.y), MSUB(a.z, b.x, a.x, b.z), MSUB(a.x, b.y, a.y, b.x));
+}
+/* base:44-46  Normalize(x) = (1/sqrt(dot(x,x))) * x */
+static inline V3 normalize3(V3 a) { float s = 1.0f / sqrtf(dot3(a, a)); return vscale(a, s); }
+
+/* OpenCL fmin/fmax: NaN-ignoring */
+static inline float cl_fmin(float x, float y) { if (x != x) return y; if (y != y) return x; return y < x ? y : x; }
+static inline float cl_fmax(float x, float y) { if (x != x) return y; if (y != y) return x; return x < y ? y : x; }
+/* convert_int / (int) cast: truncation; out-of-range saturates, NaN -> 0 (GPU behaviour) */
+static inline int f2i_rz_sat(float f) {
+    if (f != f) return 0;
+    if (f >= 2147483648.0f) return 2147483647;
+    if (f <= -2147483648.0f) return (-2147483647 - 1);
+    return (int)f;
+}
+static inline uint8_t f2u8_rz_sat(float f) {
+    if (f != f) return 0;
+    if (f >= 255.0f) return 255;
+    if (f <= 0.0f) return 0;
+    return (uint8_t)(int)f;
+}
+
+/* ------------------------------------------------------------------------- RNG */
+typedef struct { uint32_t x0, x1, c0, c1; } Rng;
+
+/* base:26-34 */
+uint32_t oracle_randomize_id(uint32_t id) {
+    id = (id ^ 61u) ^ (id >> 16);
+    id *= 9u;
+    id = id ^ (id >> 4);
+    id *= 0x27d4eb2du;
+    id = id ^ (id >> 15);
+    return id;
+}
+
+/* base:37-41 — the same hash is XOR-ed into all four words */
+static inline Rng rng_seed(const uint32_t seeds[4], uint32_t gid) {
+    uint32_t h = oracle_randomize_id(gid);
+    Rng r = {seeds[0] ^ h, seeds[1] ^ h, seeds[2] ^ h, seeds[3] ^ h};
+    return r;
+}
+
+/* base:12-23.  Per lane: res = x^c; hi = mul_hi(x,A); x = x*A + c; c = hi + (x < c ? 0xFFFFFFFF : 0)
+ * — vector compare yields -1, convert_uint2 wraps, so the "carry" ADDS 0xFFFFFFFF (not 1).
+ * Returned value: 0.0f + float(res) * ((1.0f - 0.0f) / 4294967295) where the integer literal is a
+ * 64-bit long that converts to 2^32 as float, i.e. float(res) * 2^-32 (round-to-nearest-even cvt). */
+static inline void rng_next(Rng *s, float *u0, float *u1, uint32_t *raw0, uint32_t *raw1) {
+    const uint32_t A = 4294883355u;
+    uint32_t r0 = s->x0 ^ s->c0, r1 = s->x1 ^ s->c1;
+    uint32_t hi0 = (uint32_t)(((uint64_t)s->x0 * A) >> 32), hi1 = (uint32_t)(((uint64_t)s->x1 * A) >> 32);
+    uint32_t nx0 = s->x0 * A + s->c0, nx1 = s->x1 * A + s->c1;
+    uint32_t nc0 = hi0 + (nx0 < s->c0 ? 0xFFFFFFFFu : 0u), nc1 = hi1 + (nx1 < s->c1 ? 0xFFFFFFFFu : 0u);
+    s->x0 = nx0; s->x1 = nx1; s->c0 = nc0; s->c1 = nc1;
+    const float scale = (1.0f - 0.0f) / 4294967296.0f;
+    *u0 = 0.0f + (float)r0 * scale;
+    *u1 = 0.0f + (float)r1 * scale;
+    if (raw0) *raw0 = r0;
+    if (raw1) *raw1 = r1;
+}
+
+void oracle_rng_kat(const uint32_t seeds[4], uint32_t gid, int nsteps, float *out_f, uint32_t *out_u32,
+                    uint32_t out_state[4]) {
+    Rng s = rng_seed(seeds, gid);
+    for (int k = 0; k < nsteps; ++k) {
+        float a, b; uint32_t ra, rb;
+        rng_next(&s, &a, &b, &ra, &rb);
+        if (out_f) { out_f[2 * k] = a; out_f[2 * k + 1] = b; }
+        if (out_u32) { out_u32[2 * k] = ra; out_u32[2 * k + 1] = rb; }
+    }
+    out_state[0] = s.x0; out_state[1] = s.x1; out_state[2] = s.c0; out_state[3] = s.c1;
+}
+
+/* ----------------------------------------------------------------------- scene */
+typedef struct {
+    int carry;               /* 0: base (t reset per TraceRay, no r<t on the floor), 1: lmem family */
+    int skip_zero_light;     /* base:171 */
+    int use_grid;
+    const int32_t *spheres, *squares;
+    const float *tris; int ntris;
+    const float (*lights)[4]; int nlights;
+    V3 box_min, box_max; int res[3]; V3 cell;
+    const uint32_t *cell_start, *cell_refs;
+} Scene;
+
+/* base:111-134 / grid:61-85 — Moller-Trumbore on one triangle; returns 1 if *t improved */
+static inline int triangle_intersect(const float *tri, V3 o, V3 d, float *t, V3 *n, oracle_counters *cnt) {
+    cnt->tri_tests++;
+    V3 v0 = v3(tri[0], tri[1], tri[2]), v1 = v3(tri[4], tri[5], tri[6]), v2 = v3(tri[8], tri[9], tri[10]);
+    V3 e0 = vsub(v1, v0), e2 = vsub(v2, v0);
+    V3 pvec = cross3(d, e2);
+    float det = dot3(e0, pvec);
+    if (fabsf(det) < 0.01f) return 0;
+    float inv = 1.0f / det;
+    V3 tvec = vsub(o, v0);
+    float u = dot3(tvec, pvec) * inv;
+    if (u < 0.0f || u > 1.0f) return 0;
+    V3 qvec = cross3(tvec, e0);
+    float v = dot3(d, qvec) * inv;
+    if (v < 0.0f || u + v > 1.0f) return 0;
+    float r = dot3(e2, qvec) * inv;
+    if (r < *t) {                      /* no lower bound on r (base:129) */
+        *t = r;
+        *n = normalize3(cross3(e0, e2));
+        return 1;
+    }
+    return 0;
+}
+
+/* floor, squares, spheres: base:64-108 / lmem:63-106 / grid:112-156 */
+static inline int trace_analytic(const Scene *S, V3 o, V3 d, float *t, V3 *n, oracle_counters *cnt) {
+    int m = 0;
+    float r = -o.z / d.z;
+    if (S->carry ? (0.01f < r && r < *t) : (0.01f < r)) { *t = r; *n = v3(0, 0, 1); m = 1; }
+    for (int k = 19; k--;)
+        for (int j = 9; j--;)
+            if (S->squares[j] & (1 << k)) {
+                cnt->prim_tests++;
+                r = ((float)(4 + j) - o.z) / d.z;
+                V3 P = vmadd(d, r, o);
+                if (r < *t && fabsf((float)k - P.x) < 1.0f && fabsf(P.y) < 1.0f) { *t = r; *n = v3(0, 0, 1); m = 3; }
+            }
+    for (int k = 19; k--;)
+        for (int j = 9; j--;)
+            if (S->spheres[j] & (1 << k)) {
+                cnt->prim_tests++;
+                V3 p = v3(o.x + (float)(-k), o.y + 0.0f, o.z + (float)(-j - 4));
+                float b = dot3(p, d);
+                float c = dot3(p, p) - 1.0f;
+                float q = MADD(b, b, -c);
+                if (q > 0.0f) {
+                    r = -b - sqrtf(q);
+                    if (r < *t && r > 0.01f) { *t = r; *n = normalize3(vmadd(d, *t, p)); m = 3; }
+                }
+            }
+    return m;
+}
+
+static inline float comp(V3 v, int a) { return a == 0 ? v.x : (a == 1 ? v.y : v.z); }
+
+/* grid:157-198 */
+static inline int trace_grid(const Scene *S, V3 o, V3 d, float *t, V3 *n, int m, oracle_counters *cnt) {
+    float tE[3], tX[3], dl[3], next[3];
+    int idx[3], step[3], stop[3];
+    for (int a = 0; a < 3; ++a) {
+        float inv = 1.0f / comp(d, a);
+        float l1 = (comp(S->box_min, a) - comp(o, a)) * inv;
+        float l2 = (comp(S->box_max, a) - comp(o, a)) * inv;
+        tE[a] = cl_fmin(l1, l2);
+        tX[a] = cl_fmax(l1, l2);
+    }
+    float t0 = cl_fmax(cl_fmax(tE[0], tE[1]), cl_fmax(tE[0], tE[2]));
+    float t1 = cl_fmin(cl_fmin(tX[0], tX[1]), cl_fmin(tX[0], tX[2]));
+    if (t0 > t1) return m;
+    int inside = o.x >= S->box_min.x && o.x <= S->box_max.x && o.y >= S->box_min.y && o.y <= S->box_max.y &&
+                 o.z >= S->box_min.z && o.z <= S->box_max.z;
+    V3 p = inside ? o : vmadd(d, t0, o);
+    for (int a = 0; a < 3; ++a) {
+        int hi = S->res[a] - 1;
+        int v = f2i_rz_sat((comp(p, a) - comp(S->box_min, a)) / comp(S->cell, a));
+        idx[a] = v < 0 ? 0 : (v > hi ? hi : v);   /* clamp(x,lo,hi) = min(max(x,lo),hi) */
+        dl[a] = (tX[a] - tE[a]) / (float)S->res[a];
+        int pos = comp(d, a) > 0.0f;
+        next[a] = pos ? MADD((float)(idx[a] + 1), dl[a], tE[a]) : MADD((float)(S->res[a] - idx[a]), dl[a], tE[a]);
+        step[a] = pos ? 1 : -1;
+        stop[a] = pos ? S->res[a] : -1;
+    }
+    static const unsigned char map[8] = {2, 1, 2, 1, 2, 2, 0, 0};
+    for (;;) {
+        size_t ci = (size_t)idx[2] * S->res[0] * S->res[1] + (size_t)idx[1] * S->res[0] + idx[0];
+        cnt->cells_visited++;
+        uint32_t b = S->cell_start[ci], e = S->cell_start[ci + 1];
+        int found = 0;
+        for (uint32_t k = b; k < e; ++k)
+            if (triangle_intersect(S->tris + 12 * (size_t)S->cell_refs[k], o, d, t, n, cnt)) found = 1;
+        if (found) m = 4;
+        int kk = ((next[0] < next[1]) << 2) + ((next[0] < next[2]) << 1) + (next[1] < next[2]);
+        int axis = map[kk];
+        next[axis] += dl[axis];
+        if (*t < next[axis]) break;      /* compared AFTER the increment (grid:194-195) */
+        idx[axis] += step[axis];
+        if (idx[axis] == stop[axis]) break;
+    }
+    return m;
+}
+
+static inline int trace_ray(const Scene *S, V3 o, V3 d, float *t, V3 *n, oracle_counters *cnt) {
+    cnt->rays++;
+    if (!S->carry) *t = 1e9f;            /* base:52 */
+    int m = trace_analytic(S, o, d, t, n, cnt);
+    if (S->use_grid) return trace_grid(S, o, d, t, n, m, cnt);
+    for (int i = 0; i < S->ntris; ++i)
+        if (triangle_intersect(S->tris + 12 * (size_t)i, o, d, t, n, cnt)) m = 4;
+    return m;
+}
+
+/* base:139-218 / lmem:138-216 / grid:203-283.  The 5-iteration loop always returns in iteration 1
+ * because TraceRay only yields materials 0,1,3,4. */
+static inline V3 sample(const Scene *S, V3 o, V3 d, Rng *rng, oracle_counters *cnt) {
+    cnt->samples++;
+    float t = 1e9f;                       /* lmem:155 (base resets inside TraceRay anyway) */
+    V3 n = v3(0, 0, 0), dummy;
+    int m = trace_ray(S, o, d, &t, &n, cnt);
+    if (!m) {
+        float p = POW4(1.0f - d.z);
+        return v3(0.7f * p, 0.6f * p, 1.0f * p);
+    }
+    V3 X = vmadd(d, t, o);
+    float illum = 0.0f;
+    for (int i = 0; i < S->nlights; ++i) {
+        float r0, r1;
+        rng_next(rng, &r0, &r1, NULL, NULL);          /* drawn before any skip (base:168) */
+        float I = S->lights[i][3];
+        if (S->skip_zero_light && I == 0.0f) continue; /* base:171 only */
+        V3 L = v3(S->lights[i][0], S->lights[i][1], S->lights[i][2]);
+        /* light_pos + (r0,r1,0,0) + intersection*(-1) */
+        V3 ld = v3((L.x + r0) + X.x * -1.0f, (L.y + r1) + X.y * -1.0f, (L.z + 0.0f) + X.z * -1.0f);
+        ld = normalize3(ld);
+        float lam = dot3(ld, n);
+        if (lam < 0.0f) continue;
+        cnt->shadow_rays++;
+        if (trace_ray(S, X, ld, &t, &dummy, cnt)) continue;
+        V3 dv = vsub(L, X);
+        float dist = sqrtf(dot3(dv, dv));
+        float f = I / (dist * dist);
+        f = 1.0f < f ? 1.0f : f;                      /* min(x, 1.0f) = 1.0f < x ? 1.0f : x */
+        illum = MADD(lam, f, illum);
+    }
+    if (illum > 1.0f) illum = 1.0f;
+    illum /= 4.0f;
+    if (m == 1) {
+        V3 Y = vscale(X, 0.2f);
+        int odd = f2i_rz_sat(ceilf(Y.x) + ceilf(Y.y)) & 1;
+        return odd ? v3(3.0f * illum, 1.0f * illum, 1.0f * illum) : v3(3.0f * illum, 3.0f * illum, 3.0f * illum);
+    }
+    if (m == 3) return v3(2.0f * illum, 3.0f * illum, 2.0f * illum);
+    /* m == 4: facing ratio, lighting ignored (base:203-205) */
+    float fr = dot3(n, v3(-d.x, -d.y, -d.z));
+    fr = 0.0f < fr ? fr : 0.0f;                       /* max(0.0f, x) = 0.0f < x ? x : 0.0f */
+    return v3(fr, fr, fr);
+}
+
+/* base:233-236 — thin-lens camera ray for pixel column i, row j */
+static inline void camera_ray(const oracle_job *J, Rng *rng, int i, int j, V3 *o, V3 *d) {
+    float u0, u1, u2, u3;
+    rng_next(rng, &u0, &u1, NULL, NULL);
+    rng_next(rng, &u2, &u3, NULL, NULL);
+    V3 up = v3(J->cam_up[0], J->cam_up[1], J->cam_up[2]), right = v3(J->cam_right[0], J->cam_right[1], J->cam_right[2]);
+    V3 eye = v3(J->eye_offset[0], J->eye_offset[1], J->eye_offset[2]);
+    float a = (u0 - 0.5f) * 99.0f, b = (u1 - 0.5f) * 99.0f;
+    V3 delta = vmadd(right, b, vscale(up, a));
+    *o = v3(17.0f + delta.x, 16.0f + delta.y, 8.0f + delta.z);
+    float su = u2 + (float)i, sr = (float)j + u3;
+    V3 A = vmadd(right, sr, vscale(up, su));
+    A = v3(A.x + eye.x, A.y + eye.y, A.z + eye.z);
+    V3 nd = v3(delta.x * -1.0f, delta.y * -1.0f, delta.z * -1.0f);
+    *d = normalize3(vmadd(A, 16.0f, nd));
+}
+
+static void scene_from_job(const oracle_job *J, Scene *S) {
+    memset(S, 0, sizeof(*S));
+    S->carry = J->variant != ORACLE_BASE;
+    S->skip_zero_light = J->variant == ORACLE_BASE;
+    S->use_grid = J->variant == ORACLE_GRID;
+    S->spheres = J->spheres; S->squares = J->squares;
+    S->tris = J->triangles; S->ntris = J->ntriangles;
+    S->lights = J->lights; S->nlights = J->nlights;
+    S->box_min = v3(J->box_min[0], J->box_min[1], J->box_min[2]);
+    S->box_max = v3(J->box_max[0], J->box_max[1], J->box_max[2]);
+    S->res[0] = J->grid_res[0]; S->res[1] = J->grid_res[1]; S->res[2] = J->grid_res[2];
+    S->cell = v3(J->cell_size[0], J->cell_size[1], J->cell_size[2]);
+    S->cell_start = J->cell_start; S->cell_refs = J->cell_refs;
+}
+
+static inline void cnt_add(oracle_counters *a, const oracle_counters *b) {
+    a->samples += b->samples; a->rays += b->rays; a->shadow_rays += b->shadow_rays;
+    a->tri_tests += b->tri_tests; a->cells_visited += b->cells_visited; a->prim_tests += b->prim_tests;
+}
+
+int oracle_render(const oracle_job *J, uint8_t *rgba8, float *accum, uint32_t *rng_state, oracle_counters *counters) {
+    if (!J || J->width <= 0 || J->height <= 0 || J->spp <= 0 || J->variant < 0 || J->variant > 3) return -1;
+    if (J->variant == ORACLE_NODOF && J->spp != 64) return -1;
+    if (J->variant == ORACLE_GRID && (!J->cell_start || (!J->cell_refs && J->ntriangles > 0))) return -1;
+    Scene S;
+    scene_from_job(J, &S);
+    const int W = J->width, H = J->height;
+    int r0 = J->row_begin, r1 = J->row_end;
+    if (r1 <= 0 || r1 > H) r1 = H;
+    if (r0 < 0) r0 = 0;
+    oracle_counters total;
+    memset(&total, 0, sizeof(total));
+    const float scale = 224.0f / (float)J->spp;      /* = 3.5f at the reference's 64 spp */
+#ifdef _OPENMP
+    int nthreads = J->nthreads > 0 ? J->nthreads : omp_get_max_threads();
+#pragma omp parallel num_threads(nthreads)
+#endif
+    {
+        oracle_counters cnt;
+        memset(&cnt, 0, sizeof(cnt));
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 1)
+#endif
+        for (int j = r0; j < r1; ++j) {
+            for (int i = 0; i < W; ++i) {
+                float col[4];
+                size_t pix = (size_t)j * W + i;
+                if (J->variant != ORACLE_NODOF) {
+                    /* base:224-240 */
+                    Rng rng = rng_seed(J->seeds, (uint32_t)(j * W + i));
+                    V3 c = v3(13.0f, 13.0f, 13.0f);
+                    for (int r = J->spp; r--;) {
+                        V3 o, d;
+                        camera_ray(J, &rng, i, j, &o, &d);
+                        V3 s = sample(&S, o, d, &rng, &cnt);
+                        c = v3(MADD(s.x, scale, c.x), MADD(s.y, scale, c.y), MADD(s.z, scale, c.z));
+                    }
+                    col[0] = c.x; col[1] = c.y; col[2] = c.z;
+                    if (rng_state) {
+                        uint32_t *q = rng_state + 4 * pix;
+                        q[0] = rng.x0; q[1] = rng.x1; q[2] = rng.c0; q[3] = rng.c1;
+                    }
+                } else {
+                    /* nodof:217-250 then 253-274: 8x8 work-items per pixel, each its own stream */
+                    V3 acc[64];
+                    for (int ly = 0; ly < 8; ++ly)
+                        for (int lx = 0; lx < 8; ++lx) {
+                            int gi = 8 * i + lx, gj = 8 * j + ly;
+                            uint32_t gid = (uint32_t)(gj * (8 * W) + gi);
+                            Rng rng = rng_seed(J->seeds, gid);
+                            V3 o, d;
+                            camera_ray(J, &rng, i, j, &o, &d);
+                            V3 s = sample(&S, o, d, &rng, &cnt);
+                            acc[ly * 8 + lx] = vscale(s, 3.5f);
+                            if (rng_state) {
+                                uint32_t *q = rng_state + 4 * (size_t)gid;
+                                q[0] = rng.x0; q[1] = rng.x1; q[2] = rng.c0; q[3] = rng.c1;
+                            }
+                        }
+                    for (int working = 32; working > 0; working >>= 1)
+                        for (int li = 0; li < working; ++li) {
+                            acc[li].x += acc[li + working].x;
+                            acc[li].y += acc[li + working].y;
+                            acc[li].z += acc[li + working].z;
+                        }
+                    col[0] = acc[0].x + 13.0f; col[1] = acc[0].y + 13.0f; col[2] = acc[0].z + 13.0f;
+                }
+                col[3] = 255.0f;
+                if (accum) memcpy(accum + 4 * pix, col, sizeof(col));
+                if (rgba8)
+                    for (int k = 0; k < 4; ++k) rgba8[4 * pix + k] = f2u8_rz_sat(col[k]);
+            }
+        }
+#ifdef _OPENMP
+#pragma omp critical
+#endif
+        cnt_add(&total, &cnt);
+    }
+    if (counters) *counters = total;
+    return 0;
+}
+
+int oracle_trace_ray(int carry, const float o[3], const float d[3], float *t_inout, float n_out[3],
+                     const int32_t spheres[9], const int32_t squares[9], const float *tris12, int ntris) {
+    Scene S;
+    memset(&S, 0, sizeof(S));
+    S.carry = carry; S.spheres = spheres; S.squares = squares; S.tris = tris12; S.ntris = ntris;
+    oracle_counters cnt;
+    memset(&cnt, 0, sizeof(cnt));
+    V3 n = v3(0, 0, 0);
+    int m = trace_ray(&S, v3(o[0], o[1], o[2]), v3(d[0], d[1], d[2]), t_inout, &n, &cnt);
+    n_out[0] = n.x; n_out[1] = n.y; n_out[2] = n.z;
+    return m;
+}
