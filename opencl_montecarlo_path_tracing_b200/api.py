@@ -1,0 +1,272 @@
+"""Python face of the CLSuperPathTracer drop-in (thin: everything real happens behind the C ABI).
+
+    scene = load_scene_dir("scenes/_gen/base", variant="base")      # the reference's .txt files
+    with Renderer(device=0) as r:
+        r.set_scene(scene)
+        out = r.render(variant="base", width=512, height=512, seeds=(1, 2, 3, 4))
+        out.image  # (H, W, 4) uint8 == what the reference writes into result.ppm
+
+Host-side steps (parsing, camera, grid sizing) call libpthost.so, the same C code the drop-in
+executables use; rendering calls libptcuda.so.  No CPU fallback exists.
+"""
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from ._lib import PT_ARITH, PT_KERNEL, PT_SCENE_MEM, PT_VARIANT, pt_camera, pt_counters, pt_grid, pt_render_params, pt_scene
+
+
+class PtError(RuntimeError):
+    pass
+
+
+def _check(rc, what):
+    if rc:
+        raise PtError("%s failed: %s" % (what, _lib.cuda_lib().pt_last_error().decode()))
+
+
+@dataclass
+class Scene:
+    spheres: np.ndarray                      # int32[9]
+    squares: np.ndarray                      # int32[9]
+    triangles: np.ndarray                    # float32[n, 12]  (v0 v1 v2 as float4, w = 0)
+    lights: np.ndarray                       # float32[nlights, 4]
+    box_min: np.ndarray = field(default_factory=lambda: np.zeros(4, np.float32))
+    box_max: np.ndarray = field(default_factory=lambda: np.zeros(4, np.float32))
+
+    @property
+    def ntriangles(self):
+        return int(self.triangles.shape[0])
+
+    def to_c(self):
+        s = pt_scene()
+        s.spheres[:] = [int(v) for v in self.spheres]
+        s.squares[:] = [int(v) for v in self.squares]
+        self._tri_keepalive = np.ascontiguousarray(self.triangles, dtype=np.float32).reshape(-1)
+        s.triangles = self._tri_keepalive.ctypes.data_as(C.POINTER(C.c_float))
+        s.ntriangles = self.ntriangles
+        s.nlights = int(self.lights.shape[0])
+        for i in range(s.nlights):
+            for k in range(4):
+                s.lights[i][k] = float(self.lights[i, k])
+        return s
+
+
+def default_max_triangles(variant):
+    """MAX_TRIANGLES of the reference hosts (CLSuperPathTracer.c:14; trianglegrid :15)."""
+    return 65536 if variant == "grid" else 512
+
+
+def load_scene_dir(path, variant="base", max_triangles=None, triangles_file="triangles.txt"):
+    """Parse spheres.txt / squares.txt (planes.txt for nodof) / triangles.txt / lights.txt of a directory
+    with the drop-in's own C parsers (reference semantics incl. the feof() quirks)."""
+    h = _lib.host_lib()
+    if max_triangles is None:
+        max_triangles = default_max_triangles(variant)
+
+    def bitmap(name):
+        arr = (C.c_int32 * 9)()
+        if h.pth_parse_bitmap(os.path.join(path, name).encode(), arr) < 0:
+            raise FileNotFoundError(os.path.join(path, name))
+        return np.array(arr[:], dtype=np.int32)
+
+    spheres = bitmap("spheres.txt")
+    sq_name = "squares.txt"
+    if variant == "nodof" and os.path.exists(os.path.join(path, "planes.txt")):
+        sq_name = "planes.txt"
+    squares = bitmap(sq_name)
+    ptr = C.POINTER(C.c_float)()
+    bmin, bmax = (C.c_float * 4)(), (C.c_float * 4)()
+    n = h.pth_parse_triangles(os.path.join(path, triangles_file).encode(), max_triangles, C.byref(ptr), bmin, bmax)
+    if n < 0:
+        raise FileNotFoundError(os.path.join(path, triangles_file))
+    tris = np.ctypeslib.as_array(ptr, shape=(max(n, 1) * 12,))[: n * 12].copy().reshape(n, 12)
+    C.CDLL(None).free(ptr)
+    lights_c = ((C.c_float * 4) * 5)()
+    nl = h.pth_parse_lights(os.path.join(path, "lights.txt").encode(), C.byref(lights_c), 0)
+    if nl < 0:
+        raise FileNotFoundError(os.path.join(path, "lights.txt"))
+    lights = np.array([[lights_c[i][k] for k in range(4)] for i in range(nl)], dtype=np.float32).reshape(nl, 4)
+    return Scene(spheres, squares, tris, lights, np.array(bmin[:], np.float32), np.array(bmax[:], np.float32))
+
+
+def camera():
+    """The four camera kernel arguments (CLSuperPathTracer.c:236-243)."""
+    cam = pt_camera()
+    _lib.host_lib().pth_camera(C.byref(cam))
+    return cam
+
+
+def grid_dims(scene, cell_size_modifier=3.0):
+    g = pt_grid()
+    bmin = (C.c_float * 4)(*[float(v) for v in scene.box_min])
+    bmax = (C.c_float * 4)(*[float(v) for v in scene.box_max])
+    _lib.host_lib().pth_grid_dims(bmin, bmax, scene.ntriangles, C.c_float(cell_size_modifier), C.byref(g))
+    return g
+
+
+def save_pam(path, image):
+    img = np.ascontiguousarray(image, dtype=np.uint8)
+    hgt, wid = img.shape[:2]
+    if _lib.host_lib().pth_save_pam(path.encode(), wid, hgt, img.ctypes.data_as(C.c_void_p)):
+        raise PtError("error writing %s" % path)
+
+
+@dataclass
+class RenderResult:
+    image: np.ndarray                 # (H, W, 4) uint8
+    ms: float                         # device time of the launch (CUDA events)
+    counters: dict
+    accum: np.ndarray = None          # (H, W, 4) float32 if requested
+    rng_state: np.ndarray = None      # (items, 4) uint32 if requested
+
+
+def make_params(variant, width, height, seeds, spp=64, kernel="mega", scene_mem=None, arith="fma", rows=None,
+                want_accum=False, want_rng=False, interleave=0, rank=0, nranks=1):
+    p = pt_render_params()
+    p.variant = PT_VARIANT[variant]
+    p.width, p.height, p.spp = int(width), int(height), int(spp)
+    if rows is not None:
+        p.row_begin, p.row_end = int(rows[0]), int(rows[1])
+    p.seeds[:] = [int(s) & 0xFFFFFFFF for s in seeds]
+    p.kernel = PT_KERNEL[kernel]
+    if scene_mem is None:
+        scene_mem = "const" if variant == "base" else "smem"
+    p.scene_mem = PT_SCENE_MEM[scene_mem]
+    p.arith = PT_ARITH[arith]
+    p.want_accum, p.want_rng = int(bool(want_accum)), int(bool(want_rng))
+    p.row_interleave, p.rank, p.nranks = int(interleave), int(rank), int(nranks)
+    return p
+
+
+class Renderer:
+    """One pt_ctx: one CUDA device, one stream."""
+
+    def __init__(self, device=0, stream=None):
+        self._l = _lib.cuda_lib()
+        if self._l.pt_device_count() <= 0:
+            raise PtError("no CUDA device visible; libptcuda has no CPU fallback")
+        self.ctx = self._l.pt_create_on_stream(device, C.c_void_p(stream)) if stream is not None else self._l.pt_create(device)
+        if not self.ctx:
+            raise PtError("pt_create failed: %s" % self._l.pt_last_error().decode())
+        self.device = device
+        self._scene = None
+        self.cam = camera()
+
+    def close(self):
+        if self.ctx:
+            self._l.pt_destroy(self.ctx)
+            self.ctx = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def device_props(self):
+        sm, khz = C.c_int(), C.c_int()
+        self._l.pt_device_props(self.ctx, C.byref(sm), C.byref(khz))
+        name = C.create_string_buffer(256)
+        self._l.pt_device_name(self.ctx, name, 256)
+        return {"name": name.value.decode(), "sm_count": sm.value, "clock_khz": khz.value}
+
+    def set_scene(self, scene):
+        self._scene = scene
+        cs = scene.to_c()
+        _check(self._l.pt_set_scene(self.ctx, C.byref(cs)), "pt_set_scene")
+
+    def build_grid(self, grid):
+        evt = self._l.pt_build_grid(self.ctx, C.byref(grid))
+        if not evt:
+            raise PtError("pt_build_grid failed: %s" % self._l.pt_last_error().decode())
+        ms = self._l.pt_runtime_ms(evt)
+        self._l.pt_release_event(evt)
+        self._grid = grid
+        return ms
+
+    def read_grid_csr(self):
+        total = C.c_uint64()
+        _check(self._l.pt_read_grid_csr(self.ctx, None, None, C.byref(total)), "pt_read_grid_csr")
+        g = self._grid
+        ncells = g.res[0] * g.res[1] * g.res[2]
+        start = np.zeros(ncells + 1, np.uint32)
+        refs = np.zeros(max(int(total.value), 1), np.uint32)
+        _check(self._l.pt_read_grid_csr(self.ctx, start.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                        refs.ctypes.data_as(C.POINTER(C.c_uint32)), None), "pt_read_grid_csr")
+        return start, refs[: int(total.value)]
+
+    def read_grid_cells(self):
+        g = self._grid
+        ncells = g.res[0] * g.res[1] * g.res[2]
+        raw = np.zeros(ncells * 128, np.uint8)
+        _check(self._l.pt_read_grid_cells(self.ctx, raw.ctypes.data_as(C.c_void_p), ncells), "pt_read_grid_cells")
+        return raw.reshape(ncells, 128)
+
+    def render(self, variant, width, height, seeds, read_image=True, **kw):
+        p = make_params(variant, width, height, seeds, **kw)
+        evt = self._l.pt_launch_pathtracer(self.ctx, C.byref(self.cam), C.byref(p))
+        if not evt:
+            raise PtError("pt_launch_pathtracer failed: %s" % self._l.pt_last_error().decode())
+        image = None
+        if read_image:
+            ptr = self._l.pt_map_render(self.ctx, None)
+            if not ptr:
+                raise PtError("pt_map_render failed: %s" % self._l.pt_last_error().decode())
+            image = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(height, width, 4)).copy()
+        ms = self._l.pt_runtime_ms(evt)
+        self._l.pt_release_event(evt)
+        cnt = pt_counters()
+        _check(self._l.pt_get_counters(self.ctx, C.byref(cnt)), "pt_get_counters")
+        res = RenderResult(image=image, ms=ms, counters=cnt.as_dict())
+        if p.want_accum:
+            acc = np.zeros((height, width, 4), np.float32)
+            _check(self._l.pt_read_accum(self.ctx, acc.ctypes.data_as(C.POINTER(C.c_float)), acc.size), "pt_read_accum")
+            res.accum = acc
+        if p.want_rng:
+            items = width * height * (64 if variant == "nodof" else 1)
+            st = np.zeros((items, 4), np.uint32)
+            _check(self._l.pt_read_rng_state(self.ctx, st.ctypes.data_as(C.POINTER(C.c_uint32)), st.size), "pt_read_rng_state")
+            res.rng_state = st
+        return res
+
+    def render_device(self, variant, width, height, seeds, d_rgba8, d_accum=None, **kw):
+        """Render into caller-owned device memory (raw pointers, e.g. torch tensors' data_ptr())."""
+        p = make_params(variant, width, height, seeds, **kw)
+        _check(self._l.pt_render_device(self.ctx, C.byref(self.cam), C.byref(p), C.c_void_p(d_rgba8),
+                                        C.c_void_p(d_accum) if d_accum else None), "pt_render_device")
+
+    def tonemap_device(self, d_accum, d_rgba8, width, height):
+        _check(self._l.pt_tonemap_device(self.ctx, C.c_void_p(d_accum), C.c_void_p(d_rgba8), width, height), "pt_tonemap_device")
+
+    def counters(self):
+        cnt = pt_counters()
+        _check(self._l.pt_get_counters(self.ctx, C.byref(cnt)), "pt_get_counters")
+        return cnt.as_dict()
+
+    def synchronize(self):
+        _check(self._l.pt_synchronize(self.ctx), "pt_synchronize")
+
+    def probe_trace(self, variant, origins, dirs, t_in, arith="fma"):
+        o = np.ascontiguousarray(origins, np.float32)
+        d = np.ascontiguousarray(dirs, np.float32)
+        t = np.ascontiguousarray(t_in, np.float32).copy()
+        n = o.shape[0]
+        m = np.zeros(n, np.int32)
+        nrm = np.zeros((n, 3), np.float32)
+        fp = C.POINTER(C.c_float)
+        _check(self._l.pt_probe_trace(self.ctx, PT_VARIANT[variant], PT_ARITH[arith], n, o.ctypes.data_as(fp), d.ctypes.data_as(fp),
+                                      t.ctypes.data_as(fp), m.ctypes.data_as(C.POINTER(C.c_int32)), nrm.ctypes.data_as(fp)),
+               "pt_probe_trace")
+        return m, t, nrm
+
+    def probe_rng(self, seeds, gid, nsteps):
+        s = (C.c_uint32 * 4)(*[int(v) for v in seeds])
+        out = np.zeros(2 * nsteps, np.float32)
+        st = np.zeros(4, np.uint32)
+        _check(self._l.pt_probe_rng(self.ctx, s, gid, nsteps, out.ctypes.data_as(C.POINTER(C.c_float)),
+                                    st.ctypes.data_as(C.POINTER(C.c_uint32))), "pt_probe_rng")
+        return out, st

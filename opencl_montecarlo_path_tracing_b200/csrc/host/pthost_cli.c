@@ -1,0 +1,171 @@
+/*
+ * pthost_cli.c — the drop-in command-line programs.  One driver, parameterised by variant, reproduces
+ * the argv, the scene files read from the current directory, the stdout lines (in order) and the
+ * result.ppm of the four reference mains:
+ *   CLSuperPathTracer/CLSuperPathTracer.c:186-339            (PT_VARIANT_BASE)
+ *   CLSuperPathTracer_lmem/CLSuperPathTracer.c:195-354       (PT_VARIANT_LMEM)
+ *   CLSuperPathTracer_lmem_NoDoF/CLSuperPathTracer.c:219-394 (PT_VARIANT_NODOF)
+ *   CLSuperPathTracer_trianglegrid/CLSuperPathTracer.c:383-583 (PT_VARIANT_GRID)
+ * Where the reference talks to OpenCL through ocl_boiler.h, this talks to libptcuda.so (ptcuda.h).
+ *
+ * Extensions are env-only so the command line stays a drop-in:
+ *   PT_SEEDS=a,b,c,d   fixed seeds (default: wall-clock recipe of the reference)
+ *   PT_SPP=n           samples per pixel (default 64)
+ *   PT_KERNEL=mega|persistent|wavefront     PT_SCENE_MEM=const|smem     PT_ARITH=fma|separate
+ *   PT_MAX_TRIANGLES=n lift the 512 / 65536 MAX_TRIANGLES cap of the reference hosts
+ *   PT_DEVICE / OCL_DEVICE   device index
+ *   PT_STATS=1         append Mrays/s, samples/s and work counters after the reference's own lines
+ */
+#define _GNU_SOURCE
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "pthost.h"
+
+static int env_choice(const char *name, const char *const *opts, int nopts, int dflt) {
+    const char *v = getenv(name);
+    if (!v || !v[0]) return dflt;
+    for (int i = 0; i < nopts; ++i)
+        if (!strcmp(v, opts[i])) return i;
+    fprintf(stderr, "%s=%s not understood\n", name, v);
+    exit(1);
+}
+
+int pth_cli_main(int variant, int argc, char **argv) {
+    int img_width = 512, img_height = 512;
+    float cell_size_modifier = 3.0f;
+    const int grid = variant == PT_VARIANT_GRID, nodof = variant == PT_VARIANT_NODOF;
+    const int samples_per_pixel_nodof = 64;
+
+    if (grid)
+        printf("Usage: %s [img_width] [img_height] [CELL_SIZE_MODIFIER]\nLoads data from triangles.txt, lights.txt, spheres.txt and squares.txt\n", argv[0]);
+    else if (nodof)
+        printf("Usage: %s [img_width] [img_height]\nLoads data from triangles.txt, lights.txt, spheres.txt and planes.txt", argv[0]);
+    else
+        printf("Usage: %s [img_width] [img_height]\nLoads data from triangles.txt, lights.txt, spheres.txt and squares.txt\n", argv[0]);
+    if (argc > 1) img_width = atoi(argv[1]);
+    if (argc > 2) img_height = atoi(argv[2]);
+    if (grid && argc > 3) cell_size_modifier = (float)atof(argv[3]);
+
+    /* select_platform / select_device / create_* of ocl_boiler.h */
+    printf("number of platforms: %u\n", 1u);
+    printf("selected platform %d: %s\n", 0, "NVIDIA CUDA (libptcuda, sm_100a)");
+    int dev = pt_select_device();
+    pt_ctx ctx = pt_create(dev);
+    time_t now = time(NULL);
+    printf("compiling:\n// %s#include \"%s\"\n", ctime(&now), "pathtracer.ocl");
+    printf("=== BUILD LOG ===\n%s\n=========\n", "kernels are precompiled CUDA for sm_100a (libptcuda.so); nothing to build\n");
+
+    uint32_t seeds[4];
+    pth_seeds(seeds);
+    printf("Seeds: %d, %d, %d, %d\n", (int)seeds[0], (int)seeds[1], (int)seeds[2], (int)seeds[3]);
+
+    long data_size = (long)img_width * img_height * 4;
+    printf("Processing image %dx%d with data size %ld bytes\n", img_width, img_height, data_size);
+
+    pt_camera cam;
+    pth_camera(&cam);
+    printf(grid ? "Cam values:\nCam_forward %f %f %f\nCam_up %f %f %f\nCam_right %f %f %f\neye_offset %f %f %f\n"
+                : "Cam values:\nCam_forward %f %f %f\nCam_up %f %f %f\nCam_right %f %f %f\n eye_offset %f %f %f\n",
+           cam.cam_forward[0], cam.cam_forward[1], cam.cam_forward[2], cam.cam_up[0], cam.cam_up[1], cam.cam_up[2],
+           cam.cam_right[0], cam.cam_right[1], cam.cam_right[2], cam.eye_offset[0], cam.eye_offset[1], cam.eye_offset[2]);
+
+    pt_scene scene;
+    memset(&scene, 0, sizeof(scene));
+    int max_triangles = grid ? 65536 : 512;     /* MAX_TRIANGLES of the respective host */
+    if (getenv("PT_MAX_TRIANGLES")) max_triangles = atoi(getenv("PT_MAX_TRIANGLES"));
+    if (pth_parse_bitmap("spheres.txt", scene.spheres) < 0) pt_check(1, "open spheres.txt");
+    const char *squares_file = "squares.txt";
+    if (nodof) {
+        /* the NoDoF host opens planes.txt, which its directory does not ship; accept either name */
+        FILE *probe = fopen("planes.txt", "r");
+        if (probe) { fclose(probe); squares_file = "planes.txt"; }
+    }
+    if (pth_parse_bitmap(squares_file, scene.squares) < 0) pt_check(1, "open %s", squares_file);
+
+    float *tris = NULL;
+    float box_min[4], box_max[4];
+    pt_grid gdesc;
+    memset(&gdesc, 0, sizeof(gdesc));
+    scene.ntriangles = pth_parse_triangles("triangles.txt", max_triangles, &tris, box_min, box_max);
+    if (scene.ntriangles < 0) pt_check(1, "open triangles.txt");
+    scene.triangles = tris;
+    if (grid) {
+        printf("Triangles bounding box values:\nvmax: %f %f %f, vmin: %f %f %f\n", box_max[0], box_max[1], box_max[2],
+               box_min[0], box_min[1], box_min[2]);
+        pth_grid_dims(box_min, box_max, scene.ntriangles, cell_size_modifier, &gdesc);
+        printf("Triangles grid size: %d x %d x %d\n", gdesc.res[0], gdesc.res[1], gdesc.res[2]);
+    }
+    scene.nlights = pth_parse_lights("lights.txt", scene.lights, variant != PT_VARIANT_BASE);
+    if (scene.nlights < 0) pt_check(1, "open lights.txt");
+    printf("Number of triangles: %d\n", scene.ntriangles);
+    printf("Number of lights: %d\n", scene.nlights);
+
+    pt_set_scene(ctx, &scene);
+    pt_event grid_evt = NULL;
+    if (grid) grid_evt = pt_build_grid(ctx, &gdesc);
+
+    static const char *const kernels[] = {"mega", "persistent", "wavefront"};
+    static const char *const mems[] = {"const", "smem"};
+    static const char *const ariths[] = {"separate", "fma"};
+    pt_render_params rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.variant = variant;
+    rp.width = img_width;
+    rp.height = img_height;
+    rp.spp = getenv("PT_SPP") ? atoi(getenv("PT_SPP")) : 64;
+    memcpy(rp.seeds, seeds, sizeof(seeds));
+    rp.kernel = env_choice("PT_KERNEL", kernels, 3, PT_KERNEL_MEGA);
+    rp.scene_mem = env_choice("PT_SCENE_MEM", mems, 2, variant == PT_VARIANT_BASE ? PT_SCENE_CONST : PT_SCENE_SMEM);
+    rp.arith = env_choice("PT_ARITH", ariths, 2, PT_ARITH_FMA);
+
+    pt_event render_evt = pt_launch_pathtracer(ctx, &cam, &rp);
+    pt_event read_evt = NULL;
+    void *pixels = pt_map_render(ctx, &read_evt);
+
+    const char *image_name = "result.ppm";
+    if (pth_save_pam(image_name, img_width, img_height, pixels) != 0) {
+        fprintf(stderr, "error writing %s\n", image_name);
+        exit(1);
+    } else
+        printf("\nSuccessfully created render image %s in the current directory\n\n", image_name);
+
+    double render_ms = pt_runtime_ms(render_evt), read_ms = pt_runtime_ms(read_evt);
+    if (grid) {
+        double grid_ms = pt_runtime_ms(grid_evt);
+        size_t grid_bytes = (size_t)128 * gdesc.res[0] * gdesc.res[1] * gdesc.res[2];
+        printf("init triangles grid : %d cells in %gms: %g GB/s\n", gdesc.res[0] * gdesc.res[1] * gdesc.res[2], grid_ms,
+               grid_bytes / 1.0e6 / grid_ms);
+    }
+    if (nodof) {
+        /* the reduction is fused into the render kernel: its separate time is 0 */
+        printf("rendering : %d pixels (with %d samples) in %gms: %g GB/s\n", img_width * img_height, samples_per_pixel_nodof,
+               render_ms, data_size * samples_per_pixel_nodof * sizeof(float) / 1.0e6 / render_ms);
+        printf("reduce img samples : %d pixels (with %d samples) in %gms: %g GB/s\n", img_width * img_height,
+               samples_per_pixel_nodof, 0.0, data_size / 1.0e6 / render_ms);
+    } else
+        printf("rendering : %d pixels in %gms: %g GB/s\n", img_width * img_height, render_ms, data_size / 1.0e6 / render_ms);
+    printf("read render data : %ld uchar in %gms: %g GB/s\n", data_size, read_ms, data_size / 1.0e6 / read_ms);
+    printf("\nTotal time: %g ms.\n", render_ms + read_ms);
+
+    if (getenv("PT_STATS")) {
+        pt_counters c;
+        pt_get_counters(ctx, &c);
+        printf("PT_STATS {\"variant\": %d, \"width\": %d, \"height\": %d, \"spp\": %d, \"kernel\": \"%s\", \"scene_mem\": \"%s\", "
+               "\"arith\": \"%s\", \"render_ms\": %.6f, \"samples\": %llu, \"rays\": %llu, \"shadow_rays\": %llu, "
+               "\"tri_tests\": %llu, \"cells_visited\": %llu, \"prim_tests\": %llu, \"mrays_per_s\": %.3f, \"msamples_per_s\": %.3f}\n",
+               variant, img_width, img_height, rp.spp, kernels[rp.kernel], mems[rp.scene_mem], ariths[rp.arith], render_ms,
+               (unsigned long long)c.samples, (unsigned long long)c.rays, (unsigned long long)c.shadow_rays,
+               (unsigned long long)c.tri_tests, (unsigned long long)c.cells_visited, (unsigned long long)c.prim_tests,
+               c.rays / 1.0e3 / render_ms, c.samples / 1.0e3 / render_ms);
+    }
+
+    pt_release_event(render_evt);
+    pt_release_event(read_evt);
+    pt_release_event(grid_evt);
+    free(tris);
+    pt_destroy(ctx);
+    return 0;
+}

@@ -1,0 +1,240 @@
+// pt_gridbuild.cuh — deterministic uniform-grid build on the device.
+//
+// Replaces kernel initTrianglesGrid (grid:311-330) + atomic_addTriangle (grid:285-289).  The reference
+// bins with atomic_inc, so the order of a cell's entries changes from run to run and `nels` keeps
+// counting past the 62-entry capacity (CellIntersect then reads out of bounds).  Here:
+//   1. count  : one thread per triangle adds 1 to every overlapped cell (same cell range arithmetic),
+//   2. scan   : exclusive prefix sum of the raw counts,
+//   3. fill   : triangle ids scattered into their cell's raw segment (arbitrary order),
+//   4. sort   : every cell sorts its segment ascending => triangle-id order, i.e. exactly what the
+//               reference's serial initTrianglesGrid_host (..._trianglegrid/CLSuperPathTracer.c:233-265)
+//               produces; the first `cap` (62) entries are kept,
+//   5. scan + emit : capped CSR (cell -> first record, count) and CONTIGUOUS per-cell triangle records
+//               (v0, e0, e2 as 3 x float4), so a traversal step reads one dense block instead of
+//               chasing 16-bit indices into a triangle array.  32-bit ids: no 65536-triangle limit.
+#pragma once
+#include "pt_host.h"
+
+namespace pt {
+
+PT_DEV void tri_cell_range(const float *t, const GridDev &G, int lo[3], int hi[3]) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float mn = cl_fmin(t[a], cl_fmin(t[4 + a], t[8 + a]));
+        float mx = cl_fmax(t[a], cl_fmax(t[4 + a], t[8 + a]));
+        int l = f2i_rz_sat(__fdiv_rn(__fsub_rn(mn, G.bmin[a]), G.cell[a]));
+        int h = f2i_rz_sat(__fdiv_rn(__fsub_rn(mx, G.bmin[a]), G.cell[a]));
+        lo[a] = min(max(l, 0), G.res[a] - 1);
+        hi[a] = min(max(h, 0), G.res[a] - 1);
+    }
+}
+
+__global__ void k_grid_count(const float *__restrict__ tris, int ntri, GridDev G, uint32_t *__restrict__ count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ntri) return;
+    int lo[3], hi[3];
+    tri_cell_range(tris + 12 * (size_t)i, G, lo, hi);
+    for (int z = lo[2]; z <= hi[2]; ++z)
+        for (int y = lo[1]; y <= hi[1]; ++y)
+            for (int x = lo[0]; x <= hi[0]; ++x)
+                atomicAdd(&count[(size_t)z * G.res[0] * G.res[1] + (size_t)y * G.res[0] + x], 1u);
+}
+
+__global__ void k_grid_fill(const float *__restrict__ tris, int ntri, GridDev G, const uint32_t *__restrict__ start,
+                            uint32_t *__restrict__ cursor, uint32_t *__restrict__ refs) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ntri) return;
+    int lo[3], hi[3];
+    tri_cell_range(tris + 12 * (size_t)i, G, lo, hi);
+    for (int z = lo[2]; z <= hi[2]; ++z)
+        for (int y = lo[1]; y <= hi[1]; ++y)
+            for (int x = lo[0]; x <= hi[0]; ++x) {
+                size_t c = (size_t)z * G.res[0] * G.res[1] + (size_t)y * G.res[0] + x;
+                uint32_t pos = atomicAdd(&cursor[c], 1u);
+                refs[start[c] + pos] = (uint32_t)i;
+            }
+}
+
+// Exclusive scan of n uint32 values, 3 passes (per-block scan, scan of block sums by one block, add).
+// `out` receives n+1 offsets.  If cap > 0 the inputs are clamped to cap first.
+constexpr int SCAN_BLOCK = 1024;
+
+__global__ void k_scan_blocks(const uint32_t *__restrict__ in, size_t n, uint32_t cap, uint32_t *__restrict__ out,
+                              uint32_t *__restrict__ block_sums) {
+    __shared__ uint32_t warp_sums[32];
+    size_t i = (size_t)blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    uint32_t v = i < n ? in[i] : 0u;
+    if (cap && v > cap) v = cap;
+    uint32_t x = v;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, off);
+        if (lane >= off) x += y;
+    }
+    if (lane == 31) warp_sums[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = warp_sums[lane];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, w, off);
+            if (lane >= off) w += y;
+        }
+        warp_sums[lane] = w;
+    }
+    __syncthreads();
+    uint32_t incl = x + (warp ? warp_sums[warp - 1] : 0u);
+    if (i < n) out[i] = incl - v;
+    if (threadIdx.x == SCAN_BLOCK - 1) block_sums[blockIdx.x] = incl;
+}
+
+__global__ void k_scan_sums(uint32_t *block_sums, int nblocks) {
+    // single block, serial over chunks of 1024 (nblocks <= 2048 for 128^3 cells)
+    __shared__ uint32_t carry;
+    __shared__ uint32_t warp_sums[32];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < nblocks; base += SCAN_BLOCK) {
+        int i = base + threadIdx.x;
+        uint32_t v = i < nblocks ? block_sums[i] : 0u;
+        uint32_t x = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, off);
+            if (lane >= off) x += y;
+        }
+        if (lane == 31) warp_sums[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = warp_sums[lane];
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                uint32_t y = __shfl_up_sync(0xffffffffu, w, off);
+                if (lane >= off) w += y;
+            }
+            warp_sums[lane] = w;
+        }
+        __syncthreads();
+        uint32_t incl = x + (warp ? warp_sums[warp - 1] : 0u) + carry;
+        if (i < nblocks) block_sums[i] = incl - v;   // exclusive
+        __syncthreads();
+        if (threadIdx.x == SCAN_BLOCK - 1) carry = incl;
+        __syncthreads();
+    }
+}
+
+__global__ void k_scan_add(uint32_t *__restrict__ out, size_t n, const uint32_t *__restrict__ block_sums,
+                           const uint32_t *__restrict__ in, uint32_t cap) {
+    size_t i = (size_t)blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    if (i < n) out[i] += block_sums[blockIdx.x];
+    if (i == n - 1) {   // total goes to out[n]
+        uint32_t v = in[i];
+        if (cap && v > cap) v = cap;
+        out[n] = out[i] + v;
+    }
+}
+
+// One thread per cell: sort the raw segment ascending (insertion sort; segments are short), keep the
+// first `cap` ids, emit capped refs + contiguous triangle records + the (first, count) cell word.
+__global__ void k_grid_emit(const float *__restrict__ tris, size_t ncells, uint32_t cap,
+                            const uint32_t *__restrict__ raw_start, uint32_t *__restrict__ raw_refs,
+                            const uint32_t *__restrict__ cap_start, uint32_t *__restrict__ refs,
+                            float4 *__restrict__ recs, uint2 *__restrict__ cells) {
+    size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    uint32_t b = raw_start[c], e = raw_start[c + 1];
+    for (uint32_t i = b + 1; i < e; ++i) {
+        uint32_t key = raw_refs[i];
+        uint32_t j = i;
+        while (j > b && raw_refs[j - 1] > key) { raw_refs[j] = raw_refs[j - 1]; --j; }
+        raw_refs[j] = key;
+    }
+    uint32_t n = e - b;
+    if (n > cap) n = cap;
+    uint32_t first = cap_start[c];
+    cells[c] = make_uint2(first, n);
+    for (uint32_t k = 0; k < n; ++k) {
+        uint32_t id = raw_refs[b + k];
+        refs[first + k] = id;
+        const float *t = tris + 12 * (size_t)id;
+        float4 *r = recs + 3 * (size_t)(first + k);
+        float e0x = __fsub_rn(t[4], t[0]), e0y = __fsub_rn(t[5], t[1]), e0z = __fsub_rn(t[6], t[2]);
+        float e2x = __fsub_rn(t[8], t[0]), e2y = __fsub_rn(t[9], t[1]), e2z = __fsub_rn(t[10], t[2]);
+        r[0] = make_float4(t[0], t[1], t[2], e0x);
+        r[1] = make_float4(e0y, e0z, e2x, e2y);
+        r[2] = make_float4(e2z, __uint_as_float(id), 0.f, 0.f);
+    }
+}
+
+static int exclusive_scan(pt_ctx ctx, const uint32_t *in, size_t n, uint32_t cap, uint32_t *out, uint32_t *block_sums) {
+    int nblocks = (int)((n + SCAN_BLOCK - 1) / SCAN_BLOCK);
+    k_scan_blocks<<<nblocks, SCAN_BLOCK, 0, ctx->stream>>>(in, n, cap, out, block_sums);
+    k_scan_sums<<<1, SCAN_BLOCK, 0, ctx->stream>>>(block_sums, nblocks);
+    k_scan_add<<<nblocks, SCAN_BLOCK, 0, ctx->stream>>>(out, n, block_sums, in, cap);
+    PT_CUDA(cudaGetLastError(), "grid scan");
+    return 0;
+}
+
+}  // namespace pt
+
+int pt_grid_build_device(pt_ctx ctx, const pt_grid *g) {
+    using namespace pt;
+    const size_t ncells = (size_t)g->res[0] * g->res[1] * g->res[2];
+    const uint32_t cap = g->max_refs_per_cell > 0 ? (uint32_t)g->max_refs_per_cell : 62u;
+    const int ntri = ctx->ntri_total;
+    GridDev G;
+    for (int a = 0; a < 3; ++a) {
+        G.bmin[a] = g->box_min[a]; G.bmax[a] = g->box_max[a]; G.cell[a] = g->cell_size[a]; G.res[a] = g->res[a];
+    }
+    G.cells = nullptr; G.recs = nullptr;
+
+    cudaFree(ctx->d_cells); cudaFree(ctx->d_recs); cudaFree(ctx->d_refs); cudaFree(ctx->d_cell_start);
+    ctx->d_cells = nullptr; ctx->d_recs = nullptr; ctx->d_refs = nullptr; ctx->d_cell_start = nullptr;
+
+    uint32_t *d_count = nullptr, *d_raw_start = nullptr, *d_cursor = nullptr, *d_raw_refs = nullptr, *d_bsums = nullptr;
+    const int nblocks = (int)((ncells + SCAN_BLOCK - 1) / SCAN_BLOCK);
+    PT_CUDA(cudaMalloc(&d_count, ncells * 4), "alloc grid count");
+    PT_CUDA(cudaMalloc(&d_raw_start, (ncells + 1) * 4), "alloc grid start");
+    PT_CUDA(cudaMalloc(&d_cursor, ncells * 4), "alloc grid cursor");
+    PT_CUDA(cudaMalloc(&d_bsums, (size_t)(nblocks + 1) * 4), "alloc scan sums");
+    PT_CUDA(cudaMalloc(&ctx->d_cell_start, (ncells + 1) * 4), "alloc cell_start");
+    PT_CUDA(cudaMalloc(&ctx->d_cells, ncells * sizeof(uint2)), "alloc cells");
+    PT_CUDA(cudaMemsetAsync(d_count, 0, ncells * 4, ctx->stream), "memset");
+    PT_CUDA(cudaMemsetAsync(d_cursor, 0, ncells * 4, ctx->stream), "memset");
+
+    const int tb = 256, tg = (ntri + tb - 1) / tb;
+    uint32_t raw_total = 0, cap_total = 0;
+    if (ntri > 0) {
+        k_grid_count<<<tg, tb, 0, ctx->stream>>>(ctx->d_tris_raw, ntri, G, d_count);
+        PT_CUDA(cudaGetLastError(), "grid count");
+    }
+    if (exclusive_scan(ctx, d_count, ncells, 0, d_raw_start, d_bsums)) return 1;
+    if (exclusive_scan(ctx, d_count, ncells, cap, ctx->d_cell_start, d_bsums)) return 1;
+    PT_CUDA(cudaMemcpyAsync(&raw_total, d_raw_start + ncells, 4, cudaMemcpyDeviceToHost, ctx->stream), "read total");
+    PT_CUDA(cudaMemcpyAsync(&cap_total, ctx->d_cell_start + ncells, 4, cudaMemcpyDeviceToHost, ctx->stream), "read total");
+    PT_CUDA(cudaStreamSynchronize(ctx->stream), "sync grid totals");
+    PT_CUDA(cudaMalloc(&d_raw_refs, (size_t)(raw_total ? raw_total : 1) * 4), "alloc raw refs");
+    PT_CUDA(cudaMalloc(&ctx->d_refs, (size_t)(cap_total ? cap_total : 1) * 4), "alloc refs");
+    PT_CUDA(cudaMalloc(&ctx->d_recs, (size_t)(cap_total ? cap_total : 1) * 3 * sizeof(float4)), "alloc records");
+    if (ntri > 0) {
+        k_grid_fill<<<tg, tb, 0, ctx->stream>>>(ctx->d_tris_raw, ntri, G, d_raw_start, d_cursor, d_raw_refs);
+        PT_CUDA(cudaGetLastError(), "grid fill");
+    }
+    k_grid_emit<<<(unsigned)((ncells + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_tris_raw, ncells, cap, d_raw_start, d_raw_refs,
+                                                                        ctx->d_cell_start, ctx->d_refs, ctx->d_recs,
+                                                                        ctx->d_cells);
+    PT_CUDA(cudaGetLastError(), "grid emit");
+    PT_CUDA(cudaStreamSynchronize(ctx->stream), "sync grid build");
+    cudaFree(d_count); cudaFree(d_raw_start); cudaFree(d_cursor); cudaFree(d_raw_refs); cudaFree(d_bsums);
+
+    G.cells = ctx->d_cells;
+    G.recs = ctx->d_recs;
+    ctx->grid = G;
+    ctx->grid_desc = *g;
+    ctx->ncells = ncells;
+    ctx->total_refs = cap_total;
+    ctx->grid_set = true;
+    return 0;
+}

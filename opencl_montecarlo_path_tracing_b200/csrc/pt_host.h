@@ -1,0 +1,107 @@
+// pt_host.h — host-side state shared by the translation units of libptcuda.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ptcuda.h"
+#include "pt_device.cuh"
+
+namespace pt {
+
+struct LaunchArgs {
+    Camera cam;
+    uint4 seeds;
+    int W, H, spp;
+    float scale;            // 224/spp (3.5 at 64 spp)
+    int row_begin, row_end; // image rows [row_begin, row_end) are eligible
+    int nrows;              // number of (virtual) rows this launch walks (see map_row)
+    int stripe_h, rank, nranks;  // row interleave (stripe_h == 0: contiguous rows)
+    uint32_t *rgba;
+    float4 *accum;          // optional
+    uint4 *rng_out;         // optional
+    unsigned long long *counters;  // 6 x u64: samples rays shadow tri_tests cells prim_tests
+    GridDev grid;
+    const SceneBlock *gscene;      // global-memory copy of the scene block (shared-memory staging source)
+    int scene_bytes;               // bytes of the block actually used (header + prims + ntri records)
+};
+
+// virtual row -> image row (identity, or the rank's interleaved stripes)
+__host__ __device__ inline int map_row(const LaunchArgs &P, int vr) {
+    if (P.stripe_h <= 0) return P.row_begin + vr;
+    int s = vr / P.stripe_h, o = vr - s * P.stripe_h;
+    return P.row_begin + (s * P.nranks + P.rank) * P.stripe_h + o;
+}
+
+}  // namespace pt
+
+struct pt_event_s {
+    cudaEvent_t start, stop;
+    int device;
+};
+
+struct pt_ctx_s {
+    int device;
+    cudaStream_t stream;
+    bool own_stream;
+    int sm_count, clock_khz;
+    char name[256];
+
+    // scene
+    bool scene_set;
+    uint64_t scene_version;
+    pt::SceneBlock *h_scene[2];   // [PT_ARITH_SEPARATE], [PT_ARITH_FMA] (normals differ)
+    pt::SceneBlock *d_scene[2];
+    int scene_bytes;
+    float *d_tris_raw;            // ntri_total x 12 floats (grid build input)
+    int ntri_total;
+
+    // grid
+    bool grid_set;
+    pt_grid grid_desc;
+    pt::GridDev grid;
+    uint2 *d_cells;
+    float4 *d_recs;
+    uint32_t *d_refs;             // capped refs (triangle ids), CSR order
+    uint32_t *d_cell_start;       // ncells + 1
+    uint64_t total_refs;
+    size_t ncells;
+
+    // render targets owned by the context
+    uint32_t *d_rgba;
+    float4 *d_accum;
+    uint4 *d_rng;
+    size_t rgba_cap, accum_cap, rng_cap;
+    uint8_t *h_rgba;              // pinned
+    size_t h_rgba_cap;
+    unsigned long long *d_counters;
+    int last_w, last_h, last_variant;
+    size_t last_rng_items;
+
+    // wavefront / persistent scratch
+    void *d_scratch;
+    size_t scratch_cap;
+};
+
+// internal helpers (ptcuda.cu)
+int pt_fail(int err, const char *fmt, ...);
+int pt_cuda_fail(cudaError_t e, const char *what);
+#define PT_CUDA(call, what)                                       \
+    do {                                                          \
+        cudaError_t e__ = (call);                                 \
+        if (e__ != cudaSuccess) return pt_cuda_fail(e__, what);   \
+    } while (0)
+#define PT_CUDA_NULL(call, what)                                  \
+    do {                                                          \
+        cudaError_t e__ = (call);                                 \
+        if (e__ != cudaSuccess) { pt_cuda_fail(e__, what); return NULL; } \
+    } while (0)
+
+int pt_ensure_scratch(pt_ctx ctx, size_t bytes);
+// makes the scene block for `arith` current in this device's __constant__ memory (no-op if it already is)
+int pt_bind_const_scene(pt_ctx ctx, int arith);
+
+// launchers implemented in the kernel translation units
+int pt_launch_mega(pt_ctx ctx, const pt_render_params *p, const pt::LaunchArgs &args);
+int pt_launch_persistent(pt_ctx ctx, const pt_render_params *p, const pt::LaunchArgs &args);
+int pt_launch_wavefront(pt_ctx ctx, const pt_render_params *p, const pt::LaunchArgs &args);
+int pt_grid_build_device(pt_ctx ctx, const pt_grid *g);

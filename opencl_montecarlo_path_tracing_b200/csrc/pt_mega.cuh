@@ -1,0 +1,162 @@
+// pt_mega.cuh — single-launch "megakernels".
+//
+//  k_mega_pixel : base / lmem / grid variants.  One thread per pixel runs the pixel's whole sample
+//                 sequence (the per-pixel RNG stream makes samples of one pixel inherently serial,
+//                 SURVEY.md 0.3); a warp covers an 8x4 pixel tile so its 32 rays stay coherent.
+//                 Replaces kernel pathTracer of base:220-241, lmem:218-254, grid:348-381.
+//  k_mega_nodof : CLSuperPathTracer_lmem_NoDoF.  The reference launches 64 work-items per pixel, writes a
+//                 268 MB float4 scratch image and reduces it with a second kernel (nodof:217-274).
+//                 Here one warp owns one pixel: lane l traces samples l and l+32, adds them (tree level
+//                 32), and five shuffle-down steps finish the reference's exact reduction tree in
+//                 registers — no scratch image, no second launch, same float sums.
+#pragma once
+#include "pt_host.h"
+
+namespace pt {
+
+__constant__ SceneBlock c_scene;
+
+// Stage the used part of the scene block from global into shared memory (the _lmem idea, lmem:232-244,
+// without its "work-group must be at least ntriangles big" limitation).
+PT_DEV const SceneBlock *stage_scene_smem(const LaunchArgs &P, unsigned char *smem) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(P.gscene);
+    uint4 *dst = reinterpret_cast<uint4 *>(smem);
+    const int n16 = P.scene_bytes >> 4;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
+    __syncthreads();
+    return reinterpret_cast<const SceneBlock *>(smem);
+}
+
+PT_DEV void flush_counters(const LaunchArgs &P, const Counters &c, int ntri_counted, int nprims) {
+    uint32_t rays = __reduce_add_sync(0xffffffffu, c.rays);
+    uint32_t shadow = __reduce_add_sync(0xffffffffu, c.shadow);
+    uint32_t cells = __reduce_add_sync(0xffffffffu, c.cells);
+    uint32_t gtri = __reduce_add_sync(0xffffffffu, c.gtri);
+    uint32_t samples = __reduce_add_sync(0xffffffffu, c.samples);
+    if ((threadIdx.x & 31) == 0 && P.counters) {
+        atomicAdd(P.counters + 0, (unsigned long long)samples);
+        atomicAdd(P.counters + 1, (unsigned long long)rays);
+        atomicAdd(P.counters + 2, (unsigned long long)shadow);
+        atomicAdd(P.counters + 3, (unsigned long long)gtri + (unsigned long long)rays * ntri_counted);
+        atomicAdd(P.counters + 4, (unsigned long long)cells);
+        atomicAdd(P.counters + 5, (unsigned long long)rays * nprims);
+    }
+}
+
+template <int VARIANT, bool FMA, int MEM>
+__global__ void __launch_bounds__(128) k_mega_pixel(const __grid_constant__ LaunchArgs P) {
+    constexpr bool CARRY = VARIANT != PT_VARIANT_BASE;
+    constexpr bool GRID = VARIANT == PT_VARIANT_GRID;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const SceneBlock *S = (MEM == PT_SCENE_SMEM) ? stage_scene_smem(P, smem_raw) : &c_scene;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    const int vr = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    Counters cnt = {0, 0, 0, 0, 0};
+    const int j = map_row(P, vr);
+    if (i < P.W && vr < P.nrows && j < P.row_end) {
+        Rng rng = rng_seed(P.seeds, (uint32_t)(j * P.W + i));
+        float cx = 13.0f, cy = 13.0f, cz = 13.0f;
+        for (int s = 0; s < P.spp; ++s) {
+            V3 o, d;
+            camera_ray<FMA>(P.cam, rng, i, j, o, d);
+            V3 c = sample<FMA, CARRY, GRID>(S, P.grid, o, d, rng, cnt);
+            cx = Ar<FMA>::madd(c.x, P.scale, cx);
+            cy = Ar<FMA>::madd(c.y, P.scale, cy);
+            cz = Ar<FMA>::madd(c.z, P.scale, cz);
+        }
+        const size_t pix = (size_t)j * P.W + i;
+        P.rgba[pix] = pack_rgba8_rz(cx, cy, cz, 255.0f);
+        if (P.accum) P.accum[pix] = make_float4(cx, cy, cz, 255.0f);
+        if (P.rng_out) P.rng_out[pix] = make_uint4(rng.x0, rng.x1, rng.c0, rng.c1);
+    }
+    flush_counters(P, cnt, GRID ? 0 : S->ntri_counted, S->nsq + S->nsp);
+}
+
+template <bool FMA, int MEM>
+__global__ void __launch_bounds__(256) k_mega_nodof(const __grid_constant__ LaunchArgs P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const SceneBlock *S = (MEM == PT_SCENE_SMEM) ? stage_scene_smem(P, smem_raw) : &c_scene;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int px = blockIdx.x * 4 + (warp & 3);
+    const int vr = blockIdx.y * 2 + (warp >> 2);
+    Counters cnt = {0, 0, 0, 0, 0};
+    const int py = map_row(P, vr);
+    if (px < P.W && vr < P.nrows && py < P.row_end) {   // warp-uniform
+        float ax[2], ay[2], az[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int li = lane + 32 * h;                       // local id inside the 8x8 group
+            const int gi = 8 * px + (li & 7), gj = 8 * py + (li >> 3);
+            const uint32_t gid = (uint32_t)(gj * (8 * P.W) + gi);
+            Rng rng = rng_seed(P.seeds, gid);
+            V3 o, d;
+            camera_ray<FMA>(P.cam, rng, px, py, o, d);
+            V3 c = sample<FMA, true, false>(S, P.grid, o, d, rng, cnt);
+            ax[h] = __fmul_rn(c.x, 3.5f); ay[h] = __fmul_rn(c.y, 3.5f); az[h] = __fmul_rn(c.z, 3.5f);
+            if (P.rng_out) P.rng_out[gid] = make_uint4(rng.x0, rng.x1, rng.c0, rng.c1);
+        }
+        // nodof:253-274 reduction tree: li += li+32, then +16, +8, +4, +2, +1
+        float sx = __fadd_rn(ax[0], ax[1]), sy = __fadd_rn(ay[0], ay[1]), sz = __fadd_rn(az[0], az[1]);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            sx = __fadd_rn(sx, __shfl_down_sync(0xffffffffu, sx, off));
+            sy = __fadd_rn(sy, __shfl_down_sync(0xffffffffu, sy, off));
+            sz = __fadd_rn(sz, __shfl_down_sync(0xffffffffu, sz, off));
+        }
+        if (lane == 0) {
+            sx = __fadd_rn(sx, 13.0f); sy = __fadd_rn(sy, 13.0f); sz = __fadd_rn(sz, 13.0f);
+            const size_t pix = (size_t)py * P.W + px;
+            P.rgba[pix] = pack_rgba8_rz(sx, sy, sz, 255.0f);
+            if (P.accum) P.accum[pix] = make_float4(sx, sy, sz, 255.0f);
+        }
+    }
+    flush_counters(P, cnt, S->ntri_counted, S->nsq + S->nsp);
+}
+
+template <int VARIANT, bool FMA, int MEM>
+static int launch_pixel(pt_ctx ctx, const LaunchArgs &args) {
+    dim3 grid((args.W + 15) / 16, (args.nrows + 7) / 8), block(128);
+    size_t smem = MEM == PT_SCENE_SMEM ? (size_t)args.scene_bytes : 0;
+    if (smem > 48 * 1024)
+        PT_CUDA(cudaFuncSetAttribute(k_mega_pixel<VARIANT, FMA, MEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                "opt-in shared memory");
+    k_mega_pixel<VARIANT, FMA, MEM><<<grid, block, smem, ctx->stream>>>(args);
+    PT_CUDA(cudaGetLastError(), "launch k_mega_pixel");
+    return 0;
+}
+
+template <bool FMA, int MEM>
+static int launch_nodof(pt_ctx ctx, const LaunchArgs &args) {
+    dim3 grid((args.W + 3) / 4, (args.nrows + 1) / 2), block(256);
+    size_t smem = MEM == PT_SCENE_SMEM ? (size_t)args.scene_bytes : 0;
+    k_mega_nodof<FMA, MEM><<<grid, block, smem, ctx->stream>>>(args);
+    PT_CUDA(cudaGetLastError(), "launch k_mega_nodof");
+    return 0;
+}
+
+template <bool FMA, int MEM>
+static int launch_mega_am(pt_ctx ctx, int variant, const LaunchArgs &args) {
+    switch (variant) {
+        case PT_VARIANT_BASE: return launch_pixel<PT_VARIANT_BASE, FMA, MEM>(ctx, args);
+        case PT_VARIANT_LMEM: return launch_pixel<PT_VARIANT_LMEM, FMA, MEM>(ctx, args);
+        case PT_VARIANT_GRID: return launch_pixel<PT_VARIANT_GRID, FMA, MEM>(ctx, args);
+        case PT_VARIANT_NODOF: return launch_nodof<FMA, MEM>(ctx, args);
+    }
+    return pt_fail(1, "unknown variant %d", variant);
+}
+
+}  // namespace pt
+
+int pt_launch_mega(pt_ctx ctx, const pt_render_params *p, const pt::LaunchArgs &args) {
+    using namespace pt;
+    const bool fma = p->arith != PT_ARITH_SEPARATE;
+    if (p->scene_mem == PT_SCENE_SMEM)
+        return fma ? launch_mega_am<true, PT_SCENE_SMEM>(ctx, p->variant, args)
+                   : launch_mega_am<false, PT_SCENE_SMEM>(ctx, p->variant, args);
+    int rc = pt_bind_const_scene(ctx, fma ? PT_ARITH_FMA : PT_ARITH_SEPARATE);
+    if (rc) return rc;
+    return fma ? launch_mega_am<true, PT_SCENE_CONST>(ctx, p->variant, args)
+               : launch_mega_am<false, PT_SCENE_CONST>(ctx, p->variant, args);
+}

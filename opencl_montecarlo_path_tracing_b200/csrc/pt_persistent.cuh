@@ -1,0 +1,6 @@
+#pragma once
+#include "pt_host.h"
+int pt_launch_persistent(pt_ctx ctx, const pt_render_params *p, const pt::LaunchArgs &args) {
+    (void)ctx; (void)p; (void)args;
+    return pt_fail(1, "persistent kernel not built yet");
+}

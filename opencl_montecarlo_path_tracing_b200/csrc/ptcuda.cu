@@ -1,0 +1,608 @@
+// ptcuda.cu — implementation of the C ABI declared in include/ptcuda.h (libptcuda.so).
+//
+// One translation unit on purpose: the kernels share one __constant__ scene block.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 (see csrc/Makefile).
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <new>
+
+#include "pt_host.h"
+#include "pt_mega.cuh"
+#include "pt_persistent.cuh"
+#include "pt_wavefront.cuh"
+#include "pt_gridbuild.cuh"
+
+// ------------------------------------------------------------------------------------ errors
+static int g_error_mode = PT_ERRORS_EXIT;
+static thread_local char g_last_error[1024] = "";
+
+extern "C" void pt_set_error_mode(int mode) { g_error_mode = mode; }
+extern "C" const char *pt_last_error(void) { return g_last_error; }
+
+int pt_fail(int err, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    char msg[900];
+    vsnprintf(msg, sizeof(msg), fmt, ap);
+    va_end(ap);
+    snprintf(g_last_error, sizeof(g_last_error), "%s - error %d", msg, err);
+    if (g_error_mode == PT_ERRORS_EXIT) {
+        fprintf(stderr, "%s\n", g_last_error);
+        exit(1);
+    }
+    return err ? err : 1;
+}
+
+int pt_cuda_fail(cudaError_t e, const char *what) {
+    return pt_fail((int)e, "%s: %s", what, cudaGetErrorString(e));
+}
+
+extern "C" void pt_check(int err, const char *fmt, ...) {
+    if (err == 0) return;
+    va_list ap;
+    va_start(ap, fmt);
+    char msg[900];
+    vsnprintf(msg, sizeof(msg), fmt, ap);
+    va_end(ap);
+    fprintf(stderr, "%s - error %d\n", msg, err);
+    exit(1);
+}
+
+// --------------------------------------------------------------------------- device / context
+extern "C" int pt_abi_version(void) { return PTCUDA_ABI_VERSION; }
+
+extern "C" int pt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+extern "C" int pt_select_device(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return -pt_cuda_fail(e, "counting devices");
+    printf("number of devices: %u\n", (unsigned)n);
+    const char *env = getenv("PT_DEVICE");
+    if (!env || !env[0]) env = getenv("OCL_DEVICE");
+    int d = (env && env[0]) ? atoi(env) : 0;
+    if (d < 0 || d >= n) {
+        fprintf(stderr, "no device number %u", (unsigned)d);
+        exit(1);
+    }
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, d);
+    if (e != cudaSuccess) return -pt_cuda_fail(e, "device name");
+    printf("selected device %d: %s\n", d, prop.name);
+    return d;
+}
+
+static pt_ctx ctx_new(int device, cudaStream_t stream, bool own) {
+    pt_ctx c = (pt_ctx)calloc(1, sizeof(pt_ctx_s));
+    c->device = device;
+    c->stream = stream;
+    c->own_stream = own;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
+        c->sm_count = prop.multiProcessorCount;
+        c->clock_khz = prop.clockRate;
+        snprintf(c->name, sizeof(c->name), "%s", prop.name);
+    }
+    return c;
+}
+
+extern "C" pt_ctx pt_create(int device) {
+    PT_CUDA_NULL(cudaSetDevice(device), "select device");
+    cudaStream_t s;
+    PT_CUDA_NULL(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "create stream");
+    pt_ctx c = ctx_new(device, s, true);
+    PT_CUDA_NULL(cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)), "alloc counters");
+    return c;
+}
+
+extern "C" pt_ctx pt_create_on_stream(int device, void *cuda_stream) {
+    PT_CUDA_NULL(cudaSetDevice(device), "select device");
+    pt_ctx c = ctx_new(device, (cudaStream_t)cuda_stream, false);
+    PT_CUDA_NULL(cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)), "alloc counters");
+    return c;
+}
+
+struct ConstOwner { pt_ctx owner; uint64_t version; int arith; };
+static ConstOwner g_const_owner[64];
+static std::atomic<uint64_t> g_scene_version{1};
+
+extern "C" void pt_destroy(pt_ctx c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->device < 64 && g_const_owner[c->device].owner == c) g_const_owner[c->device].owner = nullptr;
+    for (int a = 0; a < 2; ++a) {
+        if (c->h_scene[a]) cudaFreeHost(c->h_scene[a]);
+        cudaFree(c->d_scene[a]);
+    }
+    cudaFree(c->d_tris_raw);
+    cudaFree(c->d_cells); cudaFree(c->d_recs); cudaFree(c->d_refs); cudaFree(c->d_cell_start);
+    cudaFree(c->d_rgba); cudaFree(c->d_accum); cudaFree(c->d_rng); cudaFree(c->d_counters); cudaFree(c->d_scratch);
+    if (c->h_rgba) cudaFreeHost(c->h_rgba);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    free(c);
+}
+
+extern "C" int pt_device_name(pt_ctx c, char *buf, size_t len) {
+    snprintf(buf, len, "%s", c->name);
+    return 0;
+}
+
+extern "C" int pt_device_props(pt_ctx c, int *sm_count, int *clock_khz) {
+    if (sm_count) *sm_count = c->sm_count;
+    if (clock_khz) *clock_khz = c->clock_khz;
+    return 0;
+}
+
+int pt_ensure_scratch(pt_ctx c, size_t bytes) {
+    if (c->scratch_cap >= bytes) return 0;
+    cudaFree(c->d_scratch);
+    c->d_scratch = nullptr;
+    c->scratch_cap = 0;
+    PT_CUDA(cudaMalloc(&c->d_scratch, bytes), "alloc scratch");
+    c->scratch_cap = bytes;
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------- scene
+// Host-side float helpers for the per-triangle normal.  They mirror pt::Ar<FMA> operation for
+// operation (fmaf / sqrtf / division are correctly rounded on the host as on the device), so the
+// stored normal is bit-identical to Normalize(cross(edge0, edge2)) evaluated per hit (base:131).
+#pragma STDC FP_CONTRACT OFF
+namespace {
+struct H3 { float x, y, z; };
+inline float h_msub(bool fma, float a, float b, float c, float d) {
+    volatile float cd = c * d;
+    if (fma) return fmaf(a, b, -cd);
+    volatile float ab = a * b;
+    return ab - cd;
+}
+inline float h_madd(bool fma, float a, float b, float c) {
+    if (fma) return fmaf(a, b, c);
+    volatile float ab = a * b;
+    return ab + c;
+}
+inline H3 h_cross(bool fma, H3 a, H3 b) {
+    H3 r = {h_msub(fma, a.y, b.z, a.z, b.y), h_msub(fma, a.z, b.x, a.x, b.z), h_msub(fma, a.x, b.y, a.y, b.x)};
+    return r;
+}
+inline float h_dot(bool fma, H3 a, H3 b) {
+    volatile float xx = a.x * b.x;
+    return h_madd(fma, a.z, b.z, h_madd(fma, a.y, b.y, xx));
+}
+inline H3 h_normalize(bool fma, H3 a) {
+    volatile float s = 1.0f / sqrtf(h_dot(fma, a, a));
+    volatile float x = a.x * s, y = a.y * s, z = a.z * s;
+    H3 r = {x, y, z};
+    return r;
+}
+}  // namespace
+
+static void decode_bitmap(const int32_t bm[9], bool sphere, float2 *out, int *n) {
+    int c = 0;
+    for (int k = 19; k--;)        // reference scan order: k = 18..0, j = 8..0 (base:73-74)
+        for (int j = 9; j--;)
+            if (bm[j] & (1 << k)) {
+                out[c].x = sphere ? (float)(-k) : (float)k;
+                out[c].y = sphere ? (float)(-j - 4) : (float)(4 + j);
+                ++c;
+            }
+    *n = c;
+}
+
+extern "C" int pt_set_scene(pt_ctx c, const pt_scene *sc) {
+    using namespace pt;
+    if (!c || !sc) return pt_fail(1, "pt_set_scene: null argument");
+    if (sc->nlights < 0 || sc->nlights > 5) return pt_fail(1, "pt_set_scene: nlights %d out of range [0,5]", sc->nlights);
+    if (sc->ntriangles < 0) return pt_fail(1, "pt_set_scene: negative triangle count");
+    PT_CUDA(cudaSetDevice(c->device), "select device");
+    PT_CUDA(cudaStreamSynchronize(c->stream), "sync before scene update");
+    for (int a = 0; a < 2; ++a) {
+        if (!c->h_scene[a]) PT_CUDA(cudaMallocHost(&c->h_scene[a], sizeof(SceneBlock)), "alloc pinned scene");
+        if (!c->d_scene[a]) PT_CUDA(cudaMalloc(&c->d_scene[a], sizeof(SceneBlock)), "alloc device scene");
+    }
+    const int nbrute = sc->ntriangles < PT_MAX_CONST_TRIS ? sc->ntriangles : PT_MAX_CONST_TRIS;
+    int kept = 0;
+    for (int a = 0; a < 2; ++a) {
+        const bool fma = a == PT_ARITH_FMA;
+        SceneBlock *S = c->h_scene[a];
+        memset(S, 0, sizeof(SceneBlock));
+        decode_bitmap(sc->squares, false, S->sq, &S->nsq);
+        decode_bitmap(sc->spheres, true, S->sp, &S->nsp);
+        S->nlights = sc->nlights;
+        for (int l = 0; l < sc->nlights; ++l)
+            S->lights[l] = make_float4(sc->lights[l][0], sc->lights[l][1], sc->lights[l][2], sc->lights[l][3]);
+        S->ntri_counted = nbrute;
+        kept = 0;
+        for (int i = 0; i < nbrute; ++i) {
+            const float *t = sc->triangles + 12 * (size_t)i;
+            volatile float e0x = t[4] - t[0], e0y = t[5] - t[1], e0z = t[6] - t[2];
+            volatile float e2x = t[8] - t[0], e2y = t[9] - t[1], e2z = t[10] - t[2];
+            // |det| = |e0 . (d x e2)| <= |e0||e2||d| with |d| = 1: a triangle whose edge-length product is
+            // below half the 0.01 cull threshold (base:118) can never pass it, for any ray — skip it.
+            double l0 = sqrt((double)e0x * e0x + (double)e0y * e0y + (double)e0z * e0z);
+            double l2 = sqrt((double)e2x * e2x + (double)e2y * e2y + (double)e2z * e2z);
+            if (l0 * l2 < 0.005) continue;
+            H3 e0 = {e0x, e0y, e0z}, e2 = {e2x, e2y, e2z};
+            H3 n = h_normalize(fma, h_cross(fma, e0, e2));
+            S->tri[3 * kept + 0] = make_float4(t[0], t[1], t[2], e0.x);
+            S->tri[3 * kept + 1] = make_float4(e0.y, e0.z, e2.x, e2.y);
+            S->tri[3 * kept + 2] = make_float4(e2.z, n.x, n.y, n.z);
+            ++kept;
+        }
+        S->ntri = kept;
+    }
+    c->scene_bytes = (int)(offsetof(SceneBlock, tri) + (size_t)kept * 48);
+    for (int a = 0; a < 2; ++a)
+        PT_CUDA(cudaMemcpyAsync(c->d_scene[a], c->h_scene[a], sizeof(SceneBlock), cudaMemcpyHostToDevice, c->stream),
+                "upload scene");
+    cudaFree(c->d_tris_raw);
+    c->d_tris_raw = nullptr;
+    c->ntri_total = sc->ntriangles;
+    if (sc->ntriangles > 0) {
+        PT_CUDA(cudaMalloc(&c->d_tris_raw, (size_t)sc->ntriangles * 48), "alloc triangles");
+        PT_CUDA(cudaMemcpyAsync(c->d_tris_raw, sc->triangles, (size_t)sc->ntriangles * 48, cudaMemcpyHostToDevice, c->stream),
+                "upload triangles");
+    }
+    PT_CUDA(cudaStreamSynchronize(c->stream), "sync scene upload");
+    c->scene_set = true;
+    c->grid_set = false;
+    c->scene_version = g_scene_version.fetch_add(1);
+    return 0;
+}
+
+int pt_bind_const_scene(pt_ctx c, int arith) {
+    if (c->device >= 64) return pt_fail(1, "device index too large");
+    ConstOwner &o = g_const_owner[c->device];
+    if (o.owner == c && o.version == c->scene_version && o.arith == arith) return 0;
+    if (o.owner && o.owner != c) PT_CUDA(cudaDeviceSynchronize(), "sync before rebinding constant scene");
+    PT_CUDA(cudaMemcpyToSymbolAsync(pt::c_scene, c->h_scene[arith], (size_t)c->scene_bytes, 0, cudaMemcpyHostToDevice, c->stream),
+            "upload constant scene");
+    o.owner = c;
+    o.version = c->scene_version;
+    o.arith = arith;
+    return 0;
+}
+
+// --------------------------------------------------------------------------------------- events
+static pt_event event_new(pt_ctx c) {
+    pt_event e = (pt_event)calloc(1, sizeof(pt_event_s));
+    e->device = c->device;
+    if (cudaEventCreate(&e->start) != cudaSuccess || cudaEventCreate(&e->stop) != cudaSuccess) {
+        pt_fail(1, "create events");
+        free(e);
+        return nullptr;
+    }
+    return e;
+}
+
+extern "C" int pt_wait(pt_event e) {
+    if (!e) return 1;
+    PT_CUDA(cudaEventSynchronize(e->stop), "wait event");
+    return 0;
+}
+
+extern "C" double pt_runtime_ms(pt_event e) {
+    if (!e) return 0.0;
+    float ms = 0.f;
+    if (cudaEventSynchronize(e->stop) != cudaSuccess) return -1.0;
+    if (cudaEventElapsedTime(&ms, e->start, e->stop) != cudaSuccess) return -1.0;
+    return (double)ms;
+}
+
+extern "C" void pt_release_event(pt_event e) {
+    if (!e) return;
+    cudaEventDestroy(e->start);
+    cudaEventDestroy(e->stop);
+    free(e);
+}
+
+extern "C" int pt_synchronize(pt_ctx c) {
+    PT_CUDA(cudaStreamSynchronize(c->stream), "synchronize");
+    return 0;
+}
+
+// ----------------------------------------------------------------------------------------- grid
+extern "C" pt_event pt_build_grid(pt_ctx c, const pt_grid *g) {
+    if (!c || !g) { pt_fail(1, "pt_build_grid: null argument"); return nullptr; }
+    if (!c->scene_set) { pt_fail(1, "pt_build_grid: call pt_set_scene first"); return nullptr; }
+    for (int a = 0; a < 3; ++a)
+        if (g->res[a] < 1 || g->res[a] > 1024) { pt_fail(1, "pt_build_grid: grid_res[%d] = %d out of range", a, g->res[a]); return nullptr; }
+    PT_CUDA_NULL(cudaSetDevice(c->device), "select device");
+    pt_event e = event_new(c);
+    if (!e) return nullptr;
+    cudaEventRecord(e->start, c->stream);
+    if (pt_grid_build_device(c, g)) { pt_release_event(e); return nullptr; }
+    cudaEventRecord(e->stop, c->stream);
+    return e;
+}
+
+extern "C" int pt_read_grid_csr(pt_ctx c, uint32_t *cell_start, uint32_t *refs, uint64_t *total_refs) {
+    if (!c->grid_set) return pt_fail(1, "pt_read_grid_csr: no grid built");
+    if (total_refs) *total_refs = c->total_refs;
+    if (cell_start) PT_CUDA(cudaMemcpy(cell_start, c->d_cell_start, (c->ncells + 1) * 4, cudaMemcpyDeviceToHost), "read cell_start");
+    if (refs && c->total_refs) PT_CUDA(cudaMemcpy(refs, c->d_refs, c->total_refs * 4, cudaMemcpyDeviceToHost), "read refs");
+    return 0;
+}
+
+extern "C" int pt_read_grid_cells(pt_ctx c, void *cells, size_t ncells) {
+    if (!c->grid_set) return pt_fail(1, "pt_read_grid_cells: no grid built");
+    if (ncells != c->ncells) return pt_fail(1, "pt_read_grid_cells: expected %zu cells", c->ncells);
+    if (c->ntri_total > 65536) return pt_fail(1, "pt_read_grid_cells: 16-bit cell format needs <= 65536 triangles");
+    uint32_t *start = (uint32_t *)malloc((ncells + 1) * 4);
+    uint32_t *refs = (uint32_t *)malloc((c->total_refs ? c->total_refs : 1) * 4);
+    int rc = pt_read_grid_csr(c, start, refs, nullptr);
+    if (!rc) {
+        unsigned char *out = (unsigned char *)cells;
+        memset(out, 0, ncells * 128);
+        for (size_t i = 0; i < ncells; ++i) {
+            uint32_t n = start[i + 1] - start[i];
+            if (n > 62) n = 62;
+            memcpy(out + 128 * i, &n, 4);
+            for (uint32_t k = 0; k < n; ++k) {
+                uint16_t id = (uint16_t)refs[start[i] + k];
+                memcpy(out + 128 * i + 4 + 2 * k, &id, 2);
+            }
+        }
+    }
+    free(start);
+    free(refs);
+    return rc;
+}
+
+// --------------------------------------------------------------------------------------- render
+static int ensure_dev(void **p, size_t *cap, size_t bytes) {
+    if (*cap >= bytes && *p) return 0;
+    cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    PT_CUDA(cudaMalloc(p, bytes), "alloc render buffer");
+    *cap = bytes;
+    return 0;
+}
+
+static int validate_params(pt_ctx c, const pt_render_params *p) {
+    if (!c->scene_set) return pt_fail(1, "render: call pt_set_scene first");
+    if (p->variant < 0 || p->variant > 3) return pt_fail(1, "render: unknown variant %d", p->variant);
+    if (p->width <= 0 || p->height <= 0) return pt_fail(1, "render: bad image size %dx%d", p->width, p->height);
+    if (p->spp <= 0) return pt_fail(1, "render: spp must be positive");
+    if (p->variant == PT_VARIANT_NODOF && p->spp != 64) return pt_fail(1, "render: the NoDoF variant is defined for 64 samples (8x8 work-items) per pixel");
+    if (p->variant == PT_VARIANT_GRID && !c->grid_set) return pt_fail(1, "render: grid variant needs pt_build_grid first");
+    if ((long long)p->width * p->height * (p->variant == PT_VARIANT_NODOF ? 64 : 1) > 0x7fffffffLL)
+        return pt_fail(1, "render: work-item ids exceed 31 bits (the reference computes them in int)");
+    return 0;
+}
+
+static int fill_args(pt_ctx c, const pt_camera *cam, const pt_render_params *p, uint32_t *d_rgba, float4 *d_accum, uint4 *d_rng,
+                     pt::LaunchArgs *A) {
+    memset(A, 0, sizeof(*A));
+    for (int k = 0; k < 3; ++k) { A->cam.up[k] = cam->cam_up[k]; A->cam.right[k] = cam->cam_right[k]; A->cam.eye[k] = cam->eye_offset[k]; }
+    A->seeds = make_uint4(p->seeds[0], p->seeds[1], p->seeds[2], p->seeds[3]);
+    A->W = p->width; A->H = p->height; A->spp = p->spp;
+    A->scale = 224.0f / (float)p->spp;
+    int rb = p->row_begin, re = p->row_end;
+    if (re <= 0 || re > p->height) re = p->height;
+    if (rb < 0) rb = 0;
+    if (rb > re) rb = re;
+    A->row_begin = rb; A->row_end = re;
+    if (p->row_interleave > 0 && p->nranks > 1) {
+        int R = re - rb, hs = p->row_interleave;
+        int nstripes = (R + hs - 1) / hs;
+        int mine = (nstripes - p->rank + p->nranks - 1) / p->nranks;
+        if (mine < 0) mine = 0;
+        A->stripe_h = hs; A->rank = p->rank; A->nranks = p->nranks;
+        A->nrows = mine * hs;
+    } else {
+        A->stripe_h = 0; A->rank = 0; A->nranks = 1;
+        A->nrows = re - rb;
+    }
+    A->rgba = d_rgba; A->accum = d_accum; A->rng_out = d_rng;
+    A->counters = c->d_counters;
+    A->grid = c->grid;
+    const int arith = p->arith != PT_ARITH_SEPARATE ? PT_ARITH_FMA : PT_ARITH_SEPARATE;
+    A->gscene = c->d_scene[arith];
+    A->scene_bytes = c->scene_bytes;
+    return 0;
+}
+
+static int dispatch(pt_ctx c, const pt_render_params *p, const pt::LaunchArgs &A) {
+    PT_CUDA(cudaMemsetAsync(c->d_counters, 0, 8 * sizeof(unsigned long long), c->stream), "clear counters");
+    if (A.nrows <= 0) return 0;
+    switch (p->kernel) {
+        case PT_KERNEL_MEGA: return pt_launch_mega(c, p, A);
+        case PT_KERNEL_PERSISTENT: return pt_launch_persistent(c, p, A);
+        case PT_KERNEL_WAVEFRONT: return pt_launch_wavefront(c, p, A);
+    }
+    return pt_fail(1, "render: unknown kernel kind %d", p->kernel);
+}
+
+extern "C" pt_event pt_launch_pathtracer(pt_ctx c, const pt_camera *cam, const pt_render_params *p) {
+    if (!c || !cam || !p) { pt_fail(1, "pt_launch_pathtracer: null argument"); return nullptr; }
+    if (validate_params(c, p)) return nullptr;
+    PT_CUDA_NULL(cudaSetDevice(c->device), "select device");
+    const size_t npix = (size_t)p->width * p->height;
+    const size_t nitems = p->variant == PT_VARIANT_NODOF ? npix * 64 : npix;
+    if (ensure_dev((void **)&c->d_rgba, &c->rgba_cap, npix * 4)) return nullptr;
+    if (p->want_accum && ensure_dev((void **)&c->d_accum, &c->accum_cap, npix * 16)) return nullptr;
+    if (p->want_rng && ensure_dev((void **)&c->d_rng, &c->rng_cap, nitems * 16)) return nullptr;
+    pt::LaunchArgs A;
+    fill_args(c, cam, p, c->d_rgba, p->want_accum ? c->d_accum : nullptr, p->want_rng ? c->d_rng : nullptr, &A);
+    const bool partial = A.nrows != p->height || A.stripe_h > 0;
+    if (partial) {
+        cudaMemsetAsync(c->d_rgba, 0, npix * 4, c->stream);
+        if (p->want_accum) cudaMemsetAsync(c->d_accum, 0, npix * 16, c->stream);
+        if (p->want_rng) cudaMemsetAsync(c->d_rng, 0, nitems * 16, c->stream);
+    }
+    pt_event e = event_new(c);
+    if (!e) return nullptr;
+    cudaEventRecord(e->start, c->stream);
+    if (dispatch(c, p, A)) { pt_release_event(e); return nullptr; }
+    cudaEventRecord(e->stop, c->stream);
+    c->last_w = p->width; c->last_h = p->height; c->last_variant = p->variant;
+    c->last_rng_items = nitems;
+    return e;
+}
+
+extern "C" int pt_render_device(pt_ctx c, const pt_camera *cam, const pt_render_params *p, void *d_rgba8, void *d_accum_f32) {
+    if (!c || !cam || !p || !d_rgba8) return pt_fail(1, "pt_render_device: null argument");
+    int rc = validate_params(c, p);
+    if (rc) return rc;
+    PT_CUDA(cudaSetDevice(c->device), "select device");
+    pt::LaunchArgs A;
+    fill_args(c, cam, p, (uint32_t *)d_rgba8, (float4 *)d_accum_f32, nullptr, &A);
+    return dispatch(c, p, A);
+}
+
+extern "C" void *pt_map_render(pt_ctx c, pt_event *evt) {
+    if (!c || !c->d_rgba || c->last_w <= 0) { pt_fail(1, "pt_map_render: nothing rendered"); return nullptr; }
+    PT_CUDA_NULL(cudaSetDevice(c->device), "select device");
+    const size_t bytes = (size_t)c->last_w * c->last_h * 4;
+    if (c->h_rgba_cap < bytes) {
+        if (c->h_rgba) cudaFreeHost(c->h_rgba);
+        c->h_rgba = nullptr;
+        PT_CUDA_NULL(cudaMallocHost(&c->h_rgba, bytes), "alloc pinned render buffer");
+        c->h_rgba_cap = bytes;
+    }
+    pt_event e = evt ? event_new(c) : nullptr;
+    if (e) cudaEventRecord(e->start, c->stream);
+    PT_CUDA_NULL(cudaMemcpyAsync(c->h_rgba, c->d_rgba, bytes, cudaMemcpyDeviceToHost, c->stream), "read render data");
+    if (e) cudaEventRecord(e->stop, c->stream);
+    PT_CUDA_NULL(cudaStreamSynchronize(c->stream), "map render buffer");
+    if (evt) *evt = e;
+    return c->h_rgba;
+}
+
+extern "C" int pt_read_accum(pt_ctx c, float *dst, size_t nfloats) {
+    if (!c->d_accum) return pt_fail(1, "pt_read_accum: last launch did not set want_accum");
+    size_t have = (size_t)c->last_w * c->last_h * 4;
+    if (nfloats < have) return pt_fail(1, "pt_read_accum: buffer too small");
+    PT_CUDA(cudaMemcpyAsync(dst, c->d_accum, have * 4, cudaMemcpyDeviceToHost, c->stream), "read accum");
+    PT_CUDA(cudaStreamSynchronize(c->stream), "sync");
+    return 0;
+}
+
+extern "C" int pt_read_rng_state(pt_ctx c, uint32_t *dst, size_t nwords) {
+    if (!c->d_rng) return pt_fail(1, "pt_read_rng_state: last launch did not set want_rng");
+    size_t have = c->last_rng_items * 4;
+    if (nwords < have) return pt_fail(1, "pt_read_rng_state: buffer too small");
+    PT_CUDA(cudaMemcpyAsync(dst, c->d_rng, have * 4, cudaMemcpyDeviceToHost, c->stream), "read rng");
+    PT_CUDA(cudaStreamSynchronize(c->stream), "sync");
+    return 0;
+}
+
+extern "C" int pt_get_counters(pt_ctx c, pt_counters *out) {
+    unsigned long long h[8];
+    PT_CUDA(cudaMemcpyAsync(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream), "read counters");
+    PT_CUDA(cudaStreamSynchronize(c->stream), "sync");
+    out->samples = h[0]; out->rays = h[1]; out->shadow_rays = h[2]; out->tri_tests = h[3];
+    out->cells_visited = h[4]; out->prim_tests = h[5];
+    return 0;
+}
+
+namespace pt {
+__global__ void k_tonemap(const float4 *__restrict__ accum, uint32_t *__restrict__ rgba, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        float4 v = accum[i];
+        rgba[i] = pack_rgba8_rz(v.x, v.y, v.z, v.w);
+    }
+}
+
+template <bool FMA>
+__global__ void k_probe_trace(int variant, int n, const float *o, const float *d, float *t, int *m, float *nrm, GridDev G) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    V3 oo = mk3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), dd = mk3(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
+    float tt = t[i];
+    V3 nn = mk3(0.f, 0.f, 0.f);
+    Counters cnt = {0, 0, 0, 0, 0};
+    int mm;
+    if (variant == PT_VARIANT_BASE) mm = trace_ray<FMA, false, true, false>(&c_scene, G, oo, dd, tt, nn, cnt);
+    else if (variant == PT_VARIANT_GRID) mm = trace_ray<FMA, true, true, true>(&c_scene, G, oo, dd, tt, nn, cnt);
+    else mm = trace_ray<FMA, true, true, false>(&c_scene, G, oo, dd, tt, nn, cnt);
+    t[i] = tt; m[i] = mm;
+    nrm[3 * i] = nn.x; nrm[3 * i + 1] = nn.y; nrm[3 * i + 2] = nn.z;
+}
+
+__global__ void k_probe_rng(uint4 seeds, uint32_t gid, int nsteps, float *out_f, uint32_t *out_state) {
+    Rng r = rng_seed(seeds, gid);
+    for (int k = 0; k < nsteps; ++k) rng_next(r, out_f[2 * k], out_f[2 * k + 1]);
+    out_state[0] = r.x0; out_state[1] = r.x1; out_state[2] = r.c0; out_state[3] = r.c1;
+}
+}  // namespace pt
+
+extern "C" int pt_tonemap_device(pt_ctx c, const void *d_accum, void *d_rgba8, int width, int height) {
+    size_t n = (size_t)width * height;
+    pt::k_tonemap<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((const float4 *)d_accum, (uint32_t *)d_rgba8, n);
+    PT_CUDA(cudaGetLastError(), "tonemap");
+    return 0;
+}
+
+extern "C" int pt_probe_trace(pt_ctx c, int variant, int arith, int n, const float *o, const float *d, float *t_inout,
+                              int32_t *m_out, float *n_out) {
+    if (!c->scene_set) return pt_fail(1, "pt_probe_trace: no scene");
+    if (variant == PT_VARIANT_GRID && !c->grid_set) return pt_fail(1, "pt_probe_trace: no grid");
+    PT_CUDA(cudaSetDevice(c->device), "select device");
+    const int ar = arith != PT_ARITH_SEPARATE ? PT_ARITH_FMA : PT_ARITH_SEPARATE;
+    int rc = pt_bind_const_scene(c, ar);
+    if (rc) return rc;
+    float *d_o, *d_d, *d_t, *d_n;
+    int *d_m;
+    PT_CUDA(cudaMalloc(&d_o, n * 12), "alloc"); PT_CUDA(cudaMalloc(&d_d, n * 12), "alloc");
+    PT_CUDA(cudaMalloc(&d_t, n * 4), "alloc"); PT_CUDA(cudaMalloc(&d_n, n * 12), "alloc");
+    PT_CUDA(cudaMalloc(&d_m, n * 4), "alloc");
+    cudaMemcpyAsync(d_o, o, n * 12, cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(d_d, d, n * 12, cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(d_t, t_inout, n * 4, cudaMemcpyHostToDevice, c->stream);
+    if (ar == PT_ARITH_FMA) pt::k_probe_trace<true><<<(n + 127) / 128, 128, 0, c->stream>>>(variant, n, d_o, d_d, d_t, d_m, d_n, c->grid);
+    else pt::k_probe_trace<false><<<(n + 127) / 128, 128, 0, c->stream>>>(variant, n, d_o, d_d, d_t, d_m, d_n, c->grid);
+    PT_CUDA(cudaGetLastError(), "probe trace");
+    cudaMemcpyAsync(t_inout, d_t, n * 4, cudaMemcpyDeviceToHost, c->stream);
+    cudaMemcpyAsync(m_out, d_m, n * 4, cudaMemcpyDeviceToHost, c->stream);
+    cudaMemcpyAsync(n_out, d_n, n * 12, cudaMemcpyDeviceToHost, c->stream);
+    PT_CUDA(cudaStreamSynchronize(c->stream), "sync probe");
+    cudaFree(d_o); cudaFree(d_d); cudaFree(d_t); cudaFree(d_n); cudaFree(d_m);
+    return 0;
+}
+
+extern "C" int pt_probe_rng(pt_ctx c, const uint32_t seeds[4], uint32_t gid, int nsteps, float *out_f, uint32_t out_state[4]) {
+    PT_CUDA(cudaSetDevice(c->device), "select device");
+    float *d_f;
+    uint32_t *d_s;
+    PT_CUDA(cudaMalloc(&d_f, (size_t)nsteps * 8 + 8), "alloc"); PT_CUDA(cudaMalloc(&d_s, 16), "alloc");
+    pt::k_probe_rng<<<1, 1, 0, c->stream>>>(make_uint4(seeds[0], seeds[1], seeds[2], seeds[3]), gid, nsteps, d_f, d_s);
+    PT_CUDA(cudaGetLastError(), "probe rng");
+    cudaMemcpyAsync(out_f, d_f, (size_t)nsteps * 8, cudaMemcpyDeviceToHost, c->stream);
+    cudaMemcpyAsync(out_state, d_s, 16, cudaMemcpyDeviceToHost, c->stream);
+    PT_CUDA(cudaStreamSynchronize(c->stream), "sync probe");
+    cudaFree(d_f); cudaFree(d_s);
+    return 0;
+}
+
+extern "C" int pt_render_host(pt_ctx c, const pt_scene *scene, const pt_grid *grid, const pt_camera *cam,
+                              const pt_render_params *p, uint8_t *rgba8_out) {
+    int rc = pt_set_scene(c, scene);
+    if (rc) return rc;
+    if (p->variant == PT_VARIANT_GRID) {
+        if (!grid) return pt_fail(1, "pt_render_host: grid variant needs a pt_grid");
+        pt_event g = pt_build_grid(c, grid);
+        if (!g) return 1;
+        pt_release_event(g);
+    }
+    pt_event e = pt_launch_pathtracer(c, cam, p);
+    if (!e) return 1;
+    void *h = pt_map_render(c, nullptr);
+    pt_release_event(e);
+    if (!h) return 1;
+    memcpy(rgba8_out, h, (size_t)p->width * p->height * 4);
+    return 0;
+}

@@ -19,8 +19,9 @@
  *   3 grid   CLSuperPathTracer_trianglegrid/ lmem semantics, triangles through the uniform grid (DDA)
  *
  * Arithmetic policy (compile-time PT_CONTRACT):
- *   0  every float operation individually rounded (what g++ makes of the reference .ocl; bit-exact
- *      against oracle/_ref);
+ *   0  every float operation individually rounded (what g++ makes of the reference .ocl; image bytes
+ *      identical to oracle/_ref; pow(x,4) is the correctly rounded x^4 where glibc's powf, which _ref
+ *      uses, may be 1 ulp off for ~1e-5 of the sky samples);
  *   1  fused multiply-adds exactly where the CUDA kernels place __fmaf_rn (DESIGN.md "contraction
  *      contract"), pow(x,4) as (x*x)*(x*x): bit-exact target for the CUDA path.  Both are legal
  *      OpenCL C behaviours (FP_CONTRACT is ON by default; pow has a 16-ulp budget).

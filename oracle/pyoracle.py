@@ -1,0 +1,189 @@
+"""ctypes access to the CPU oracle (oracle/oracle.c) — TEST INFRASTRUCTURE ONLY.
+
+Importable only from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference legs.
+The product package never imports this module.
+
+    lib = OracleLib(contract=1)          # 1: FMA policy (bit-exact target of the CUDA path), 0: separate
+    out = lib.render("base", 64, 64, (1, 2, 3, 4), scene_dict)
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+BUILD = os.path.join(HERE, "_build")
+VARIANTS = {"base": 0, "lmem": 1, "nodof": 2, "grid": 3}
+
+
+def build(force=False):
+    """Compile the oracle shared libraries with gcc (seconds)."""
+    need = force or not all(os.path.exists(os.path.join(BUILD, n)) for n in ("liboracle.so", "liboracle_fma.so", "oracle_cli"))
+    if need:
+        subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
+
+
+def cpu_has_fma():
+    try:
+        return " fma " in open("/proc/cpuinfo").read()
+    except OSError:
+        return False
+
+
+class oracle_counters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("samples", "rays", "shadow_rays", "tri_tests", "cells_visited", "prim_tests")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+class oracle_job(C.Structure):
+    _fields_ = [
+        ("variant", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("spp", C.c_int32),
+        ("row_begin", C.c_int32), ("row_end", C.c_int32),
+        ("seeds", C.c_uint32 * 4), ("spheres", C.c_int32 * 9), ("squares", C.c_int32 * 9),
+        ("triangles", C.POINTER(C.c_float)), ("ntriangles", C.c_int32),
+        ("lights", (C.c_float * 4) * 5), ("nlights", C.c_int32),
+        ("cam_up", C.c_float * 4), ("cam_right", C.c_float * 4), ("eye_offset", C.c_float * 4),
+        ("box_min", C.c_float * 4), ("box_max", C.c_float * 4), ("grid_res", C.c_int32 * 4), ("cell_size", C.c_float * 4),
+        ("cell_start", C.POINTER(C.c_uint32)), ("cell_refs", C.POINTER(C.c_uint32)),
+        ("nthreads", C.c_int32),
+    ]
+
+
+class OracleLib:
+    def __init__(self, contract=1):
+        build()
+        if contract and not cpu_has_fma():
+            raise RuntimeError("this CPU has no FMA instruction; liboracle_fma.so cannot run here")
+        self.contract = int(bool(contract))
+        self.lib = C.CDLL(os.path.join(BUILD, "liboracle_fma.so" if contract else "liboracle.so"))
+        L = self.lib
+        L.oracle_render.restype = C.c_int
+        L.oracle_render.argtypes = [C.POINTER(oracle_job), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(oracle_counters)]
+        L.oracle_contract_mode.restype = C.c_int
+        L.oracle_randomize_id.restype = C.c_uint32
+        L.oracle_randomize_id.argtypes = [C.c_uint32]
+        L.oracle_build_grid.restype = C.c_uint64
+        L.oracle_trace_ray.restype = C.c_int
+        assert L.oracle_contract_mode() == self.contract
+
+    # ---- host-side restatements -------------------------------------------------------------
+    def camera(self):
+        f, u, r, e = [(C.c_float * 4)() for _ in range(4)]
+        self.lib.oracle_camera(f, u, r, e)
+        return {k: np.array(v[:], np.float32) for k, v in (("cam_forward", f), ("cam_up", u), ("cam_right", r), ("eye_offset", e))}
+
+    def parse_array(self, path):
+        a = (C.c_int32 * 9)()
+        n = self.lib.oracle_parse_array(path.encode(), a)
+        if n < 0:
+            raise FileNotFoundError(path)
+        return np.array(a[:], np.int32), n
+
+    def parse_triangles(self, path, max_triangles):
+        buf = np.zeros((max_triangles, 12), np.float32)
+        mn, mx = (C.c_float * 4)(), (C.c_float * 4)()
+        n = self.lib.oracle_parse_triangles(path.encode(), buf.ctypes.data_as(C.c_void_p), max_triangles, mn, mx)
+        if n < 0:
+            raise FileNotFoundError(path)
+        return buf[:n].copy(), np.array(mn[:], np.float32), np.array(mx[:], np.float32)
+
+    def parse_lights(self, path):
+        l = ((C.c_float * 4) * 5)()
+        n = self.lib.oracle_parse_lights(path.encode(), l)
+        if n < 0:
+            raise FileNotFoundError(path)
+        return np.array([[l[i][k] for k in range(4)] for i in range(n)], np.float32).reshape(n, 4)
+
+    def load_scene_dir(self, path, variant, max_triangles=None):
+        if max_triangles is None:
+            max_triangles = 65536 if variant == "grid" else 512
+        sq = "planes.txt" if variant == "nodof" and os.path.exists(os.path.join(path, "planes.txt")) else "squares.txt"
+        tris, mn, mx = self.parse_triangles(os.path.join(path, "triangles.txt"), max_triangles)
+        return {"spheres": self.parse_array(os.path.join(path, "spheres.txt"))[0],
+                "squares": self.parse_array(os.path.join(path, sq))[0],
+                "triangles": tris, "lights": self.parse_lights(os.path.join(path, "lights.txt")),
+                "box_min": mn, "box_max": mx}
+
+    def grid_dims(self, box_min, box_max, ntriangles, modifier=3.0):
+        res, cell = (C.c_int32 * 4)(), (C.c_float * 4)()
+        self.lib.oracle_grid_dims((C.c_float * 4)(*box_min), (C.c_float * 4)(*box_max), int(ntriangles), C.c_float(modifier), res, cell)
+        return np.array(res[:], np.int32), np.array(cell[:], np.float32)
+
+    def build_grid(self, tris, box_min, res, cell, cap=62):
+        tris = np.ascontiguousarray(tris, np.float32)
+        ncells = int(res[0]) * int(res[1]) * int(res[2])
+        start = np.zeros(ncells + 1, np.uint32)
+        a = (tris.ctypes.data_as(C.c_void_p), C.c_int(tris.shape[0]), (C.c_float * 4)(*box_min), (C.c_int32 * 4)(*[int(x) for x in res]),
+             (C.c_float * 4)(*cell), C.c_int(cap))
+        total = self.lib.oracle_build_grid(*a, start.ctypes.data_as(C.c_void_p), None)
+        refs = np.zeros(max(int(total), 1), np.uint32)
+        self.lib.oracle_build_grid(*a, start.ctypes.data_as(C.c_void_p), refs.ctypes.data_as(C.c_void_p))
+        return start, refs[: int(total)]
+
+    # ---- device-side restatement ------------------------------------------------------------
+    def rng_kat(self, seeds, gid, nsteps):
+        f = np.zeros(2 * nsteps, np.float32)
+        u = np.zeros(2 * nsteps, np.uint32)
+        st = np.zeros(4, np.uint32)
+        self.lib.oracle_rng_kat((C.c_uint32 * 4)(*seeds), C.c_uint32(gid), nsteps, f.ctypes.data_as(C.c_void_p),
+                                u.ctypes.data_as(C.c_void_p), st.ctypes.data_as(C.c_void_p))
+        return f, u, st
+
+    def trace_ray(self, carry, o, d, t, spheres, squares, tris):
+        tris = np.ascontiguousarray(tris, np.float32)
+        tt = C.c_float(t)
+        n = (C.c_float * 3)()
+        m = self.lib.oracle_trace_ray(int(carry), (C.c_float * 3)(*o), (C.c_float * 3)(*d), C.byref(tt), n,
+                                      (C.c_int32 * 9)(*[int(x) for x in spheres]), (C.c_int32 * 9)(*[int(x) for x in squares]),
+                                      tris.ctypes.data_as(C.c_void_p), int(tris.shape[0]))
+        return m, tt.value, np.array(n[:], np.float32)
+
+    def render(self, variant, width, height, seeds, scene, spp=64, rows=None, cam=None, grid=None, want_accum=True,
+               want_rng=True, nthreads=0, modifier=3.0):
+        """scene: dict with spheres, squares, triangles (n,12), lights (nl,4) [, box_min, box_max]."""
+        J = oracle_job()
+        J.variant = VARIANTS[variant]
+        J.width, J.height, J.spp = width, height, spp
+        if rows is not None:
+            J.row_begin, J.row_end = rows
+        J.seeds[:] = [int(s) & 0xFFFFFFFF for s in seeds]
+        J.spheres[:] = [int(v) for v in scene["spheres"]]
+        J.squares[:] = [int(v) for v in scene["squares"]]
+        tris = np.ascontiguousarray(scene["triangles"], np.float32).reshape(-1, 12)
+        J.triangles = tris.ctypes.data_as(C.POINTER(C.c_float))
+        J.ntriangles = tris.shape[0]
+        lights = np.asarray(scene["lights"], np.float32).reshape(-1, 4)
+        J.nlights = lights.shape[0]
+        for i in range(J.nlights):
+            for k in range(4):
+                J.lights[i][k] = float(lights[i, k])
+        cam = cam or self.camera()
+        J.cam_up[:] = list(cam["cam_up"]); J.cam_right[:] = list(cam["cam_right"]); J.eye_offset[:] = list(cam["eye_offset"])
+        keep = None
+        if variant == "grid":
+            if grid is None:
+                res, cell = self.grid_dims(scene["box_min"], scene["box_max"], tris.shape[0], modifier)
+                grid = {"box_min": scene["box_min"], "box_max": scene["box_max"], "res": res, "cell_size": cell}
+            start, refs = self.build_grid(tris, grid["box_min"], grid["res"], grid["cell_size"])
+            if refs.size == 0:
+                refs = np.zeros(1, np.uint32)
+            keep = (start, refs)
+            J.box_min[:] = [float(x) for x in grid["box_min"]]; J.box_max[:] = [float(x) for x in grid["box_max"]]
+            J.grid_res[:] = [int(x) for x in grid["res"]]; J.cell_size[:] = [float(x) for x in grid["cell_size"]]
+            J.cell_start = start.ctypes.data_as(C.POINTER(C.c_uint32))
+            J.cell_refs = refs.ctypes.data_as(C.POINTER(C.c_uint32))
+        J.nthreads = nthreads
+        img = np.zeros((height, width, 4), np.uint8)
+        acc = np.zeros((height, width, 4), np.float32) if want_accum else None
+        items = width * height * (64 if variant == "nodof" else 1)
+        rng = np.zeros((items, 4), np.uint32) if want_rng else None
+        cnt = oracle_counters()
+        rc = self.lib.oracle_render(C.byref(J), img.ctypes.data_as(C.c_void_p), acc.ctypes.data_as(C.c_void_p) if want_accum else None,
+                                    rng.ctypes.data_as(C.c_void_p) if want_rng else None, C.byref(cnt))
+        if rc:
+            raise ValueError("oracle_render rejected the job")
+        del keep
+        return {"image": img, "accum": acc, "rng_state": rng, "counters": cnt.as_dict()}
