@@ -1,0 +1,388 @@
+#!/usr/bin/env python3
+"""Benchmark of the CLSuperPathTracer hot path (BASELINE.json metric: Mrays/s and samples/s per image).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one pass of the hot path over one image: render the workload's frame (all samples of all
+pixels) into device memory.  Default workload = BASELINE.json configs[1]: the CLSuperPathTracer_lmem_NoDoF
+scene, 512x512, 64 samples per pixel (one RNG stream per sample), on 1 B200.
+
+  value   : Mrays/s, device time (CUDA events on the launching stream, one event pair per step, L2 flushed
+            between steps), scene already resident in HBM/constant memory.  1 ray = 1 TraceRay evaluation
+            (primary + shadow), counted on the device and cross-checked against the oracle in tests/.
+  e2e     : the same metric through the reference-facing C ABI with HOST buffers: pt_render_host() =
+            scene upload (H2D) + launch + blocking read of the RGBA8 image (D2H), wall clock per step.
+  roofline: the render kernel is FP32/issue bound (scene in constant/shared memory, 4 B of output per
+            pixel), so `achieved` is algorithmic TFLOP/s = F_ray x rays / kernel time with
+            F_ray = 3 + 12 n_squares + 21 n_spheres + 58 n_triangles against the FP32 peak
+            148 SM x 128 lanes x 2 x sm_max_mhz (MEASURED_PEAKS.json gives the clock; it has no FP32 figure).
+            The HBM view of the same kernel is reported too (hbm_*).
+  cpu_baseline: the reference's own CPU run of the same frame (oracle/_ref = unmodified reference compiled
+            through oracle/refrt) or, where that build is absent, the C oracle port.
+
+N > 1 (torchrun, one process per GPU): weak scaling — the image grows to 512 x (512 N) and 8-row stripes
+are dealt round-robin to the ranks (bit-exact: seeding uses global pixel ids); each rank renders its
+stripes into a zeroed float accumulation buffer, ONE NCCL reduce sums the buffers on rank 0, rank 0
+tone-maps.  No other collective.
+"""
+import argparse
+import json
+import os
+import re
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "scenes"))
+
+SEEDS = (1, 2, 3, 4)
+
+WORKLOADS = {
+    # name: variant, scene dir variant, mesh override, W, H, spp
+    "nodof_512x512x64": dict(variant="nodof", scene="nodof", mesh=None, W=512, H=512, spp=64,
+                             desc="CLSuperPathTracer_lmem_NoDoF scene (5 spheres, 3 squares, 2 lights), 512x512, 64 spp"),
+    "base_512x512x64": dict(variant="base", scene="base", mesh=None, W=512, H=512, spp=64,
+                            desc="CLSuperPathTracer default scene (96 triangles brute force), 512x512, 64 spp"),
+    "lmem_512x512x64": dict(variant="lmem", scene="lmem", mesh=None, W=512, H=512, spp=64,
+                            desc="CLSuperPathTracer_lmem scene, 512x512, 64 spp"),
+    "grid_512x512x64": dict(variant="grid", scene="grid", mesh=None, W=512, H=512, spp=64,
+                            desc="CLSuperPathTracer_trianglegrid default scene (96 triangles, 8x5x6 grid), 512x512, 64 spp"),
+    "torus_1920x1080x1024": dict(variant="base", scene="base", mesh="torus", W=1920, H=1080, spp=1024,
+                                 desc="CLSuperPathTracer with torus.txt (32 triangles), DoF, 1920x1080, 1024 spp"),
+}
+DEFAULT_WORKLOAD = "nodof_512x512x64"
+
+
+def flops_per_ray(scene):
+    nsq = sum(bin(int(v) & 0x7FFFF).count("1") for v in scene.squares)
+    nsp = sum(bin(int(v) & 0x7FFFF).count("1") for v in scene.spheres)
+    return 3 + 12 * nsq + 21 * nsp + 58 * scene.ntriangles
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.samples.append((time.time(), [x.strip() for x in line.split(",")]))
+        except Exception:
+            pass
+
+    def finish(self, t0, t1):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, f in self.samples:
+            if ts < t0 - 0.05 or ts > t1 + 0.15 or len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            for ts, f in self.samples[-3:]:
+                try:
+                    sm.append(float(f[0])); mx.append(float(f[1]))
+                except (ValueError, IndexError):
+                    pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def scene_dir_for(w, tmp):
+    import write_scenes
+    d = os.path.join(tmp, w["scene"] + ("_" + w["mesh"] if w["mesh"] else ""))
+    write_scenes.write_variant(w["scene"], d, mesh=w["mesh"])
+    return d
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def run_reference_once(w, d, H):
+    """Run the reference's own CPU implementation of this workload once; returns (kernel_ms, kind, cores)."""
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "bin", w["variant"], "CLSuperPathTracer")
+    env = dict(os.environ, PT_SEEDS=",".join(str(s) for s in SEEDS))
+    cores = os.cpu_count() or 1
+    env.setdefault("OMP_NUM_THREADS", str(cores))
+    if os.path.exists(ref_bin) and w["spp"] == 64:
+        out = subprocess.run([ref_bin, str(w["W"]), str(H)], cwd=d, env=env, capture_output=True, text=True, check=True).stdout
+        ms = 0.0
+        for pat in (r"rendering : .* in ([0-9.eE+-]+)ms", r"reduce img samples : .* in ([0-9.eE+-]+)ms"):
+            m = re.search(pat, out)
+            if m:
+                ms += float(m.group(1))
+        return ms, "reference", cores
+    from oracle import pyoracle
+    pyoracle.build()
+    env["PT_SPP"] = str(w["spp"])
+    env["PT_OUT"] = os.path.join(d, "oracle_result.ppm")
+    out = subprocess.run([os.path.join(pyoracle.BUILD, "oracle_cli"), w["variant"], str(w["W"]), str(H)], cwd=d, env=env,
+                         capture_output=True, text=True, check=True).stdout
+    stats = json.loads(out[out.index("ORACLE_STATS") + len("ORACLE_STATS"):])
+    return stats["ms"], "port", cores
+
+
+def reference_rays(w, d, H):
+    """Ray count of the frame (same seeds) from the oracle's counters, to turn reference times into Mrays/s."""
+    from oracle import pyoracle
+    pyoracle.build()
+    env = dict(os.environ, PT_SEEDS=",".join(str(s) for s in SEEDS), PT_SPP=str(w["spp"]),
+               PT_OUT=os.path.join(d, "oracle_count.ppm"))
+    out = subprocess.run([os.path.join(pyoracle.BUILD, "oracle_cli"), w["variant"], str(w["W"]), str(H)], cwd=d, env=env,
+                         capture_output=True, text=True, check=True).stdout
+    return json.loads(out[out.index("ORACLE_STATS") + len("ORACLE_STATS"):])
+
+
+def bench_reference(args, w, wname):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # bounded sample: the reference renders the full frame only for the light default workloads;
+    # heavier ones are sampled on a band of rows and scaled by rays (work is additive over pixels).
+    with tempfile.TemporaryDirectory() as tmp:
+        d = scene_dir_for(w, tmp)
+        if w["variant"] == "nodof":
+            import shutil
+            shutil.copy(os.path.join(d, "squares.txt"), os.path.join(d, "planes.txt"))
+        H = w["H"] * max(1, args.gpus)
+        stats = reference_rays(w, d, H)
+        rays, samples = stats["rays"], stats["samples"]
+        times = []
+        kind, cores = "port", 1
+        for i in range(args.warmup + args.steps):
+            ms, kind, cores = run_reference_once(w, d, H)
+            if i >= args.warmup:
+                times.append(ms)
+    ms = sum(times) / len(times)
+    mrays = rays / 1e3 / ms
+    line = {
+        "impl": "reference", "metric": "Mrays/s", "value": mrays, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wname, "description": w["desc"], "width": w["W"], "height": H, "spp": w["spp"], "seeds": list(SEEDS)},
+        "msamples_per_s": samples / 1e3 / ms, "rays_per_step": rays, "samples_per_step": samples,
+        "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": cores, "kind": kind,
+                         "sample": "full frame, every step; kernel time as printed by the reference host (render + reduce)"},
+        "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------- our arm
+def bench_ours(args, w, wname):
+    import torch
+    import opencl_montecarlo_path_tracing_b200 as pt
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != max(1, args.gpus):
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs torchrun --nproc-per-node %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    W, H, spp = w["W"], w["H"] * world, w["spp"]
+    tmp = tempfile.TemporaryDirectory()
+    d = scene_dir_for(w, tmp.name)
+    scene = pt.load_scene_dir(d, w["variant"])
+    stream = torch.cuda.current_stream()
+    r = pt.Renderer(device=local_rank, stream=stream.cuda_stream)
+    r.set_scene(scene)
+    if w["variant"] == "grid":
+        r.build_grid(pt.grid_dims(scene))
+    kw = dict(spp=spp, kernel=args.kernel, arith="fma")
+    if args.scene_mem:
+        kw["scene_mem"] = args.scene_mem
+    if world > 1:
+        kw.update(interleave=8, rank=rank, nranks=world)
+
+    rgba = torch.zeros((H, W), dtype=torch.int32, device="cuda")
+    accum = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda") if world > 1 else None
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def step():
+        if world > 1:
+            accum.zero_()
+            r.render_device(w["variant"], W, H, SEEDS, rgba.data_ptr(), accum.data_ptr(), **kw)
+            dist.reduce(accum, dst=0)
+            if rank == 0:
+                r.tonemap_device(accum.data_ptr(), rgba.data_ptr(), W, H)
+        else:
+            r.render_device(w["variant"], W, H, SEEDS, rgba.data_ptr(), None, **kw)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    counters = r.counters()                      # this rank's share of the frame
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    t0 = time.time()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)                    # L2 flush between timed iterations (not timed)
+        starts[k].record(stream)
+        step()
+        stops[k].record(stream)
+    torch.cuda.synchronize()
+    t1 = time.time()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.finish(t0, t1)
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
+    total_ms = sum(step_ms)
+    tot = torch.tensor([total_ms, float(counters["rays"]), float(counters["samples"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = tot.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tot.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        total_ms, rays, samples = float(mx[0]), float(sm[1]), float(sm[2])
+    else:
+        rays, samples = float(tot[1]), float(tot[2])
+    ms_per_step = total_ms / args.steps
+
+    # ---- e2e through the C ABI with host buffers (rank-local frame share; N=1: the whole frame)
+    import ctypes as C
+    import numpy as np
+    from opencl_montecarlo_path_tracing_b200 import _lib
+    lib = _lib.cuda_lib()
+    r2 = pt.Renderer(device=local_rank)
+    cs = scene.to_c()
+    grid = pt.grid_dims(scene) if w["variant"] == "grid" else None
+    p = pt.make_params(w["variant"], W, H, SEEDS, **kw)
+    host_img = np.zeros((H, W, 4), np.uint8)
+    e2e_steps = max(3, min(args.steps, 50))
+    for i in range(3 + e2e_steps):
+        if i == 3:
+            r2.synchronize()
+            if world > 1:
+                dist.barrier()
+            te0 = time.perf_counter()
+        rc = lib.pt_render_host(r2.ctx, C.byref(cs), C.byref(grid) if grid else None, C.byref(r2.cam), C.byref(p),
+                                host_img.ctypes.data_as(C.POINTER(C.c_uint8)))
+        assert rc == 0, lib.pt_last_error()
+    e2e_ms = (time.perf_counter() - te0) * 1e3 / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t[0])
+    h2d = 2 * 27408 + scene.ntriangles * 48      # two arithmetic-policy scene blocks + raw triangles
+    d2h = W * H * 4
+    r2.close()
+
+    if rank == 0:
+        F = flops_per_ray(scene)
+        peaks = measured_peaks()
+        props = r.device_props()
+        sm_max = (peaks or {}).get("sm_max_mhz") or (clocks["sm_max_mhz"] or props["clock_khz"] / 1e3)
+        fp32_peak = props["sm_count"] * 128 * 2 * sm_max * 1e6 / 1e12
+        kernel_ms = ms_per_step                   # one kernel per step at N=1
+        rays_per_gpu = rays / world
+        achieved = F * rays_per_gpu / (kernel_ms * 1e-3) / 1e12
+        hbm_peak = (peaks or {}).get("hbm_gbs", 6650.0)
+        out_bytes = W * H * 4 / world
+        line = {
+            "metric": "Mrays/s", "value": rays / 1e3 / ms_per_step, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wname, "description": w["desc"], "width": W, "height": H, "spp": spp, "seeds": list(SEEDS),
+                       "kernel": args.kernel, "scene_mem": args.scene_mem or ("const" if w["variant"] == "base" else "smem"),
+                       "arith": "fma (bit-exact vs oracle -DPT_CONTRACT=1)", "l2": "flushed between timed steps (256 MiB write)",
+                       "sharding": "8-row stripes round-robin over ranks + one NCCL reduce of the float accumulation buffer"
+                       if world > 1 else "single GPU"},
+            "msamples_per_s": samples / 1e3 / ms_per_step, "rays_per_step": rays, "samples_per_step": samples,
+            "e2e": {"value": rays / 1e3 / e2e_ms, "unit": "Mrays/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "api": "pt_render_host (scene upload + launch + blocking RGBA8 read)"},
+            "gpu_launches": args.steps * (1 if world == 1 else 2),
+            "clocks": clocks,
+            "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+                         "traffic": None, "flops_per_ray": F,
+                         "peak_source": "148 SM x 128 FP32 lanes x 2 x sm_max_mhz(%s) — MEASURED_PEAKS.json has no FP32 figure" % sm_max,
+                         "hbm_achieved_gbs": out_bytes / (kernel_ms * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak,
+                         "hbm_peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s"},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                with tempfile.TemporaryDirectory() as t2:
+                    d2 = scene_dir_for(w, t2)
+                    if w["variant"] == "nodof":
+                        import shutil
+                        shutil.copy(os.path.join(d2, "squares.txt"), os.path.join(d2, "planes.txt"))
+                    ms, kind, cores = run_reference_once(w, d2, H)
+                line["cpu_baseline"] = {"value": rays / 1e3 / ms, "unit": "Mrays/s", "cores": cores, "kind": kind, "ms": ms,
+                                        "sample": "the full %dx%dx%d frame once (kernel time printed by the reference host)" % (W, H, spp)}
+            except Exception as exc:  # pragma: no cover - reporting only
+                line["cpu_baseline"] = {"error": str(exc)}
+        print(json.dumps(line))
+    r.close()
+    tmp.cleanup()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--kernel", default="mega", choices=["mega", "persistent", "wavefront"])
+    ap.add_argument("--scene-mem", default=None, choices=["const", "smem"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        if args.steps > 5:
+            args.steps = 3       # each step is seconds of CPU work; keep the whole run within minutes
+        args.warmup = min(args.warmup, 1)
+        bench_reference(args, w, args.workload)
+    else:
+        bench_ours(args, w, args.workload)
+
+
+if __name__ == "__main__":
+    main()

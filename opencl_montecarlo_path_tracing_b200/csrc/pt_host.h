@@ -21,6 +21,7 @@ struct LaunchArgs {
     uint4 *rng_out;         // optional
     unsigned long long *counters;  // 6 x u64: samples rays shadow tri_tests cells prim_tests
     GridDev grid;
+    AnalyticParams ap;             // floor/squares/spheres/lights in kernel-parameter space
     const SceneBlock *gscene;      // global-memory copy of the scene block (shared-memory staging source)
     int scene_bytes;               // bytes of the block actually used (header + prims + ntri records)
 };

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(128) k_mega_pixel(const __grid_constant__ Laun
         for (int s = 0; s < P.spp; ++s) {
             V3 o, d;
             camera_ray<FMA>(P.cam, rng, i, j, o, d);
-            V3 c = sample<FMA, CARRY, GRID>(S, P.grid, o, d, rng, cnt);
+            V3 c = sample<FMA, CARRY, GRID>(P.ap, S, P.grid, o, d, rng, cnt);
             cx = Ar<FMA>::madd(c.x, P.scale, cx);
             cy = Ar<FMA>::madd(c.y, P.scale, cy);
             cz = Ar<FMA>::madd(c.z, P.scale, cz);
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(128) k_mega_pixel(const __grid_constant__ Laun
         if (P.accum) P.accum[pix] = make_float4(cx, cy, cz, 255.0f);
         if (P.rng_out) P.rng_out[pix] = make_uint4(rng.x0, rng.x1, rng.c0, rng.c1);
     }
-    flush_counters(P, cnt, GRID ? 0 : S->ntri_counted, S->nsq + S->nsp);
+    flush_counters(P, cnt, GRID ? 0 : S->ntri_counted, P.ap.nsq + P.ap.nsp);
 }
 
 template <bool FMA, int MEM>
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(256) k_mega_nodof(const __grid_constant__ Laun
             Rng rng = rng_seed(P.seeds, gid);
             V3 o, d;
             camera_ray<FMA>(P.cam, rng, px, py, o, d);
-            V3 c = sample<FMA, true, false>(S, P.grid, o, d, rng, cnt);
+            V3 c = sample<FMA, true, false>(P.ap, S, P.grid, o, d, rng, cnt);
             ax[h] = __fmul_rn(c.x, 3.5f); ay[h] = __fmul_rn(c.y, 3.5f); az[h] = __fmul_rn(c.z, 3.5f);
             if (P.rng_out) P.rng_out[gid] = make_uint4(rng.x0, rng.x1, rng.c0, rng.c1);
         }
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) k_mega_nodof(const __grid_constant__ Laun
             if (P.accum) P.accum[pix] = make_float4(sx, sy, sz, 255.0f);
         }
     }
-    flush_counters(P, cnt, S->ntri_counted, S->nsq + S->nsp);
+    flush_counters(P, cnt, S->ntri_counted, P.ap.nsq + P.ap.nsp);
 }
 
 template <int VARIANT, bool FMA, int MEM>

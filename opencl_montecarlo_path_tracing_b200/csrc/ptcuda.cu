@@ -411,6 +411,10 @@ static int fill_args(pt_ctx c, const pt_camera *cam, const pt_render_params *p, 
     const int arith = p->arith != PT_ARITH_SEPARATE ? PT_ARITH_FMA : PT_ARITH_SEPARATE;
     A->gscene = c->d_scene[arith];
     A->scene_bytes = c->scene_bytes;
+    const pt::SceneBlock *hs = c->h_scene[arith];
+    A->ap.nsq = hs->nsq; A->ap.nsp = hs->nsp; A->ap.nlights = hs->nlights;
+    for (int i = 0; i < PT_FAST_PRIMS; ++i) { A->ap.sq[i] = hs->sq[i]; A->ap.sp[i] = hs->sp[i]; }
+    for (int i = 0; i < 5; ++i) A->ap.lights[i] = hs->lights[i];
     return 0;
 }
 
@@ -518,18 +522,26 @@ __global__ void k_tonemap(const float4 *__restrict__ accum, uint32_t *__restrict
 }
 
 template <bool FMA>
-__global__ void k_probe_trace(int variant, int n, const float *o, const float *d, float *t, int *m, float *nrm, GridDev G) {
+__global__ void k_probe_trace(int variant, int n, const float *o, const float *d, float *t, int *m, float *nrm,
+                              const __grid_constant__ LaunchArgs P) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     V3 oo = mk3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), dd = mk3(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
     float tt = t[i];
-    V3 nn = mk3(0.f, 0.f, 0.f);
     Counters cnt = {0, 0, 0, 0, 0};
-    int mm;
-    if (variant == PT_VARIANT_BASE) mm = trace_ray<FMA, false, true, false>(&c_scene, G, oo, dd, tt, nn, cnt);
-    else if (variant == PT_VARIANT_GRID) mm = trace_ray<FMA, true, true, true>(&c_scene, G, oo, dd, tt, nn, cnt);
-    else mm = trace_ray<FMA, true, true, false>(&c_scene, G, oo, dd, tt, nn, cnt);
-    t[i] = tt; m[i] = mm;
+    int hit;
+    V3 nn = mk3(0.f, 0.f, 0.f);
+    if (variant == PT_VARIANT_BASE) {
+        hit = trace_ray<FMA, false, false>(P.ap, &c_scene, P.grid, oo, dd, tt, cnt);
+        if (hit) nn = hit_normal<FMA, false>(P.ap, &c_scene, P.grid, hit, oo, dd, tt);
+    } else if (variant == PT_VARIANT_GRID) {
+        hit = trace_ray<FMA, true, true>(P.ap, &c_scene, P.grid, oo, dd, tt, cnt);
+        if (hit) nn = hit_normal<FMA, true>(P.ap, &c_scene, P.grid, hit, oo, dd, tt);
+    } else {
+        hit = trace_ray<FMA, true, false>(P.ap, &c_scene, P.grid, oo, dd, tt, cnt);
+        if (hit) nn = hit_normal<FMA, false>(P.ap, &c_scene, P.grid, hit, oo, dd, tt);
+    }
+    t[i] = tt; m[i] = hit_material(hit);
     nrm[3 * i] = nn.x; nrm[3 * i + 1] = nn.y; nrm[3 * i + 2] = nn.z;
 }
 
@@ -563,8 +575,15 @@ extern "C" int pt_probe_trace(pt_ctx c, int variant, int arith, int n, const flo
     cudaMemcpyAsync(d_o, o, n * 12, cudaMemcpyHostToDevice, c->stream);
     cudaMemcpyAsync(d_d, d, n * 12, cudaMemcpyHostToDevice, c->stream);
     cudaMemcpyAsync(d_t, t_inout, n * 4, cudaMemcpyHostToDevice, c->stream);
-    if (ar == PT_ARITH_FMA) pt::k_probe_trace<true><<<(n + 127) / 128, 128, 0, c->stream>>>(variant, n, d_o, d_d, d_t, d_m, d_n, c->grid);
-    else pt::k_probe_trace<false><<<(n + 127) / 128, 128, 0, c->stream>>>(variant, n, d_o, d_d, d_t, d_m, d_n, c->grid);
+    pt_camera cam0;
+    memset(&cam0, 0, sizeof(cam0));
+    pt_render_params rp0;
+    memset(&rp0, 0, sizeof(rp0));
+    rp0.variant = variant; rp0.width = 1; rp0.height = 1; rp0.spp = 64; rp0.arith = ar;
+    pt::LaunchArgs LA;
+    fill_args(c, &cam0, &rp0, nullptr, nullptr, nullptr, &LA);
+    if (ar == PT_ARITH_FMA) pt::k_probe_trace<true><<<(n + 127) / 128, 128, 0, c->stream>>>(variant, n, d_o, d_d, d_t, d_m, d_n, LA);
+    else pt::k_probe_trace<false><<<(n + 127) / 128, 128, 0, c->stream>>>(variant, n, d_o, d_d, d_t, d_m, d_n, LA);
     PT_CUDA(cudaGetLastError(), "probe trace");
     cudaMemcpyAsync(t_inout, d_t, n * 4, cudaMemcpyDeviceToHost, c->stream);
     cudaMemcpyAsync(m_out, d_m, n * 4, cudaMemcpyDeviceToHost, c->stream);

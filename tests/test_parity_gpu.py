@@ -35,7 +35,8 @@ def _compare(res, ref, what):
 
 @pytest.mark.parametrize("variant", ["base", "lmem", "nodof", "grid"])
 @pytest.mark.parametrize("arith", ["fma", "separate"])
-def test_bit_exact_windows(renderer, scene_dirs, oracle_fma, oracle_sep, variant, arith):
+@pytest.mark.parametrize("kernel", ["mega", "persistent"])
+def test_bit_exact_windows(renderer, scene_dirs, oracle_fma, oracle_sep, variant, arith, kernel):
     o = oracle_fma if arith == "fma" else oracle_sep
     d = scene_dirs[variant]
     scene = pt.load_scene_dir(d, variant)
@@ -45,7 +46,7 @@ def test_bit_exact_windows(renderer, scene_dirs, oracle_fma, oracle_sep, variant
         renderer.build_grid(pt.grid_dims(scene))
     W = H = 512
     for name, rows in WINDOWS.items():
-        res = renderer.render(variant, W, H, SEED_SETS[0], rows=rows, arith=arith, want_accum=True, want_rng=True)
+        res = renderer.render(variant, W, H, SEED_SETS[0], rows=rows, arith=arith, kernel=kernel, want_accum=True, want_rng=True)
         ref = o.render(variant, W, H, SEED_SETS[0], osc, rows=rows)
         r0, r1 = rows
         if variant == "nodof":
@@ -58,7 +59,7 @@ def test_bit_exact_windows(renderer, scene_dirs, oracle_fma, oracle_sep, variant
         res.rng_state, ref["rng_state"] = st.reshape(-1, 4), rst.reshape(-1, 4)
         res.accum, ref["accum"] = res.accum[r0:r1], ref["accum"][r0:r1]
         res.image, ref["image"] = res.image[r0:r1], ref["image"][r0:r1]
-        _compare(res, ref, "%s/%s/%s" % (variant, arith, name))
+        _compare(res, ref, "%s/%s/%s/%s" % (variant, arith, kernel, name))
 
 
 @pytest.mark.parametrize("variant", ["base", "lmem", "nodof", "grid"])
@@ -71,10 +72,11 @@ def test_scene_mem_and_seeds(renderer, scene_dirs, oracle_fma, variant):
         renderer.build_grid(pt.grid_dims(scene))
     W, H, rows = 640, 360, (300, 332)
     ref = oracle_fma.render(variant, W, H, SEED_SETS[1], _oracle_scene(oracle_fma, d, variant), rows=rows)
-    for mem in ("const", "smem"):
-        res = renderer.render(variant, W, H, SEED_SETS[1], rows=rows, scene_mem=mem, want_accum=True)
-        assert np.array_equal(res.image[rows[0]:rows[1]], ref["image"][rows[0]:rows[1]]), mem
-        assert np.array_equal(res.accum[rows[0]:rows[1]].view(np.uint32), ref["accum"][rows[0]:rows[1]].view(np.uint32)), mem
+    for kernel in ("mega", "persistent"):
+        for mem in ("const", "smem"):
+            res = renderer.render(variant, W, H, SEED_SETS[1], rows=rows, scene_mem=mem, kernel=kernel, want_accum=True)
+            assert np.array_equal(res.image[rows[0]:rows[1]], ref["image"][rows[0]:rows[1]]), (kernel, mem)
+            assert np.array_equal(res.accum[rows[0]:rows[1]].view(np.uint32), ref["accum"][rows[0]:rows[1]].view(np.uint32)), (kernel, mem)
 
 
 def test_torus_mesh_and_spp_extension(renderer, scene_dirs, oracle_fma):
