@@ -1,0 +1,183 @@
+#!/usr/bin/env python3
+"""Generates tests/golden/*.json|*.npz from the REFERENCE ITSELF: the unmodified reference host programs
+and kernels compiled by `make -C oracle ref` (oracle/refrt).  Only runnable in the build container
+(needs /root/reference); the outputs are committed so the pin travels.
+
+  golden_rng.json      MWC64XVEC2 / randomizeId known answers from the reference's own inline functions
+  golden_trace.npz     TraceRay(base) and TraceRay(lmem) on random rays: material, t, normal (bit patterns)
+  golden_host.json     what the reference hosts print: camera, counts, bbox, grid size; PAM header bytes
+  golden_images.npz    result.ppm of every variant for two seed sets at 512x512: SHA-256 + selected rows
+  golden_grid.npz      cell contents (sorted ids) written by the reference's initTrianglesGrid kernel
+"""
+import ctypes as C
+import hashlib
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "scenes"))
+import write_scenes  # noqa: E402
+
+REF = os.path.join(ROOT, "oracle", "_ref")
+SEED_SETS = [(1, 2, 3, 4), (123456789, 42, 7, 99999)]
+ROWS = [100, 120, 250, 300, 350, 400, 511]
+
+
+def lib(variant):
+    return C.CDLL(os.path.join(REF, "libref_%s.so" % variant))
+
+
+def rng_golden():
+    L = lib("base")
+    L.ref_probe_randomize_id.restype = C.c_uint32
+    out = {"randomize_id": {str(i): int(L.ref_probe_randomize_id(C.c_uint32(i))) for i in (0, 1, 61, 12345, 262143, 2 ** 31 - 1, 2 ** 32 - 1)},
+           "streams": []}
+    for seeds in SEED_SETS + [(0, 0, 0, 0), (134217727,) * 4]:
+        for gid in (0, 1, 12345, 262143, 16777215):
+            n = 64
+            f = (C.c_float * (2 * n))()
+            st = (C.c_uint32 * 4)()
+            L.ref_probe_rng((C.c_uint32 * 4)(*seeds), C.c_uint32(gid), n, f, st)
+            bits = np.frombuffer(bytes(f), np.uint32)
+            out["streams"].append({"seeds": list(seeds), "gid": gid, "float_bits": [int(b) for b in bits], "state": [int(s) for s in st]})
+    json.dump(out, open(os.path.join(HERE, "golden_rng.json"), "w"))
+
+
+def trace_golden(tmp):
+    rng = np.random.default_rng(20261018)
+    d = os.path.join(tmp, "lmem")
+    write_scenes.write_variant("lmem", d)
+    from oracle.pyoracle import OracleLib
+    o = OracleLib(0)
+    sc = o.load_scene_dir(d, "lmem")
+    n = 4000
+    # rays from the camera region towards the scene plus fully random ones
+    orig = np.empty((n, 3), np.float32)
+    dirs = np.empty((n, 3), np.float32)
+    orig[: n // 2] = np.array([17, 16, 8], np.float32) + rng.normal(0, 0.1, (n // 2, 3)).astype(np.float32)
+    tgt = np.stack([rng.uniform(0, 18, n // 2), rng.uniform(-2, 8, n // 2), rng.uniform(0, 13, n // 2)], 1).astype(np.float32)
+    dd = tgt - orig[: n // 2]
+    dirs[: n // 2] = dd / np.linalg.norm(dd, axis=1, keepdims=True)
+    orig[n // 2:] = np.stack([rng.uniform(0, 18, n - n // 2), rng.uniform(-3, 8, n - n // 2), rng.uniform(0.01, 13, n - n // 2)], 1)
+    dd = rng.normal(0, 1, (n - n // 2, 3))
+    dirs[n // 2:] = dd / np.linalg.norm(dd, axis=1, keepdims=True)
+    tin = np.where(rng.uniform(size=n) < 0.5, 1e9, rng.uniform(0.5, 30, n)).astype(np.float32)
+    res = {}
+    for variant in ("base", "lmem"):
+        L = lib(variant)
+        L.ref_probe_trace_ray.restype = C.c_int
+        m = np.zeros(n, np.int32); t = np.zeros(n, np.float32); nn = np.zeros((n, 3), np.float32)
+        tris = np.ascontiguousarray(sc["triangles"], np.float32)
+        for k in range(n):
+            tt = C.c_float(float(tin[k]))
+            no = (C.c_float * 3)()
+            m[k] = L.ref_probe_trace_ray((C.c_float * 3)(*orig[k]), (C.c_float * 3)(*dirs[k]), C.byref(tt), no,
+                                         (C.c_int32 * 9)(*[int(x) for x in sc["spheres"]]), (C.c_int32 * 9)(*[int(x) for x in sc["squares"]]),
+                                         tris.ctypes.data_as(C.c_void_p), tris.shape[0])
+            t[k] = tt.value
+            nn[k] = no[:]
+        res["m_" + variant] = m; res["t_" + variant] = t.view(np.uint32); res["n_" + variant] = nn.view(np.uint32)
+    np.savez_compressed(os.path.join(HERE, "golden_trace.npz"), origins=orig, dirs=dirs, t_in=tin, **res)
+
+
+def run_ref(variant, d, w, h, seeds, extra=()):
+    env = dict(os.environ, PT_SEEDS=",".join(str(s) for s in seeds))
+    out = subprocess.run([os.path.join(REF, "bin", variant, "CLSuperPathTracer"), str(w), str(h), *extra], cwd=d, env=env,
+                         capture_output=True, text=True, check=True).stdout
+    raw = open(os.path.join(d, "result.ppm"), "rb").read()
+    k = raw.index(b"ENDHDR\n") + 7
+    return out, raw[:k], np.frombuffer(raw[k:], np.uint8).reshape(h, w, 4)
+
+
+def images_and_host(tmp):
+    host = {}
+    imgs = {}
+    for variant in ("base", "lmem", "nodof", "grid"):
+        d = os.path.join(tmp, "img_" + variant)
+        write_scenes.write_variant(variant, d)
+        for si, seeds in enumerate(SEED_SETS):
+            out, hdr, img = run_ref(variant, d, 512, 512, seeds)
+            imgs["%s_s%d_sha256" % (variant, si)] = np.frombuffer(hashlib.sha256(img.tobytes()).digest(), np.uint8)
+            imgs["%s_s%d_rows" % (variant, si)] = img[ROWS].copy()
+        cam = re.search(r"Cam values:\n(.*\n.*\n.*\n.*)\n", out).group(1)
+        host[variant] = {"camera_print": cam, "ntriangles": int(re.search(r"Number of triangles: (\d+)", out).group(1)),
+                         "nlights": int(re.search(r"Number of lights: (\d+)", out).group(1)), "pam_header": hdr.decode(),
+                         "lights_print": re.findall(r"Light \d+: .*", out)}
+        if variant == "grid":
+            host[variant]["bbox_print"] = re.search(r"vmax: .*", out).group(0)
+            host[variant]["grid_size"] = [int(x) for x in re.search(r"Triangles grid size: (\d+) x (\d+) x (\d+)", out).groups()]
+    # non-square image, torus mesh, another grid modifier
+    d = os.path.join(tmp, "torus")
+    write_scenes.write_variant("base", d, mesh="torus")
+    out, hdr, img = run_ref("base", d, 640, 360, SEED_SETS[0])
+    imgs["torus_640x360_sha256"] = np.frombuffer(hashlib.sha256(img.tobytes()).digest(), np.uint8)
+    imgs["torus_640x360_rows"] = img[[150, 200, 300, 359]].copy()
+    host["torus"] = {"ntriangles": int(re.search(r"Number of triangles: (\d+)", out).group(1))}
+    d = os.path.join(tmp, "gridtorus")
+    write_scenes.write_variant("grid", d, mesh="torus")
+    out, hdr, img = run_ref("grid", d, 512, 512, SEED_SETS[0], extra=("6.5",))
+    imgs["gridtorus_m6.5_sha256"] = np.frombuffer(hashlib.sha256(img.tobytes()).digest(), np.uint8)
+    imgs["gridtorus_m6.5_rows"] = img[ROWS].copy()
+    host["gridtorus_m6.5"] = {"bbox_print": re.search(r"vmax: .*", out).group(0),
+                              "grid_size": [int(x) for x in re.search(r"Triangles grid size: (\d+) x (\d+) x (\d+)", out).groups()]}
+    imgs["rows"] = np.array(ROWS)
+    json.dump(host, open(os.path.join(HERE, "golden_host.json"), "w"), indent=1)
+    np.savez_compressed(os.path.join(HERE, "golden_images.npz"), **imgs)
+
+
+def grid_golden(tmp):
+    """Run the reference's initTrianglesGrid kernel through refrt's CL entry points and dump the cells."""
+    from oracle.pyoracle import OracleLib
+    o = OracleLib(0)
+    out = {}
+    for name, mesh, modifier in (("default", None, 3.0), ("torus", "torus", 3.0), ("torus_fine", "torus", 40.0)):
+        d = os.path.join(tmp, "g_" + name)
+        write_scenes.write_variant("grid", d, mesh=mesh)
+        sc = o.load_scene_dir(d, "grid")
+        res, cell = o.grid_dims(sc["box_min"], sc["box_max"], sc["triangles"].shape[0], modifier)
+        L = lib("grid")
+        for fn in ("clCreateKernel", "clCreateBuffer", "clCreateProgramWithSource"):
+            getattr(L, fn).restype = C.c_void_p
+        err = C.c_int()
+        k = C.c_void_p(L.clCreateKernel(None, b"initTrianglesGrid", C.byref(err)))
+        ncells = int(res[0] * res[1] * res[2])
+        cells = np.zeros(ncells * 128, np.uint8)
+        tris = np.ascontiguousarray(sc["triangles"], np.float32)
+        bc = C.c_void_p(L.clCreateBuffer(None, C.c_uint64(1 << 5), C.c_size_t(cells.nbytes), cells.ctypes.data_as(C.c_void_p), C.byref(err)))
+        bt = C.c_void_p(L.clCreateBuffer(None, C.c_uint64(1 << 5), C.c_size_t(tris.nbytes), tris.ctypes.data_as(C.c_void_p), C.byref(err)))
+        vmin = (C.c_float * 4)(*sc["box_min"]); r4 = (C.c_int32 * 4)(*[int(x) for x in res]); c4 = (C.c_float * 4)(*cell)
+        L.clSetKernelArg(k, 0, C.c_size_t(8), C.byref(bc)); L.clSetKernelArg(k, 1, C.c_size_t(8), C.byref(bt))
+        L.clSetKernelArg(k, 2, C.c_size_t(16), vmin); L.clSetKernelArg(k, 3, C.c_size_t(16), r4); L.clSetKernelArg(k, 4, C.c_size_t(16), c4)
+        gws = (C.c_size_t * 1)(tris.shape[0])
+        assert L.clEnqueueNDRangeKernel(None, k, 1, None, gws, None, 0, None, None) == 0
+        L.clEnqueueMapBuffer.restype = C.c_void_p
+        ptr = L.clEnqueueMapBuffer(None, bc, 1, 1, C.c_size_t(0), C.c_size_t(cells.nbytes), 0, None, None, C.byref(err))
+        got = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(ncells, 128)).copy()
+        nels = got[:, :4].copy().view(np.uint32).reshape(-1)
+        ids = got[:, 4:].copy().view(np.uint16).reshape(ncells, 62)
+        # atomic order is arbitrary: store each cell's ids sorted; nels may exceed 62 in the reference (overflow bug)
+        srt = np.full((ncells, 62), 65535, np.uint16)
+        for c in range(ncells):
+            n = min(int(nels[c]), 62)
+            srt[c, :n] = np.sort(ids[c, :n])
+        out[name + "_res"] = res; out[name + "_cell"] = cell.view(np.uint32); out[name + "_nels"] = nels; out[name + "_ids"] = srt
+        out[name + "_modifier"] = np.float32(modifier)
+    np.savez_compressed(os.path.join(HERE, "golden_grid.npz"), **out)
+
+
+if __name__ == "__main__":
+    sys.path.insert(0, ROOT)
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref", "oracle"])
+    with tempfile.TemporaryDirectory() as tmp:
+        rng_golden()
+        trace_golden(tmp)
+        images_and_host(tmp)
+        grid_golden(tmp)
+    print("golden vectors written to", HERE)

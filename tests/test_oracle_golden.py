@@ -1,0 +1,137 @@
+"""The oracle against the golden vectors produced by the REFERENCE ITSELF (tests/golden/make_golden.py:
+unmodified reference .c/.ocl compiled through oracle/refrt).  CPU only."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import SEED_SETS
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_rng_known_answers(oracle_sep):
+    g = json.load(open(os.path.join(G, "golden_rng.json")))
+    for k, v in g["randomize_id"].items():
+        assert oracle_sep.lib.oracle_randomize_id(int(k)) == v
+    for s in g["streams"]:
+        f, u, st = oracle_sep.rng_kat(s["seeds"], s["gid"], 64)
+        assert [int(x) for x in f.view(np.uint32)] == s["float_bits"]
+        assert [int(x) for x in st] == s["state"]
+        # first output is pixel independent: (s.x ^ s.z, s.y ^ s.w)   
+        assert int(u[0]) == s["seeds"][0] ^ s["seeds"][2] and int(u[1]) == s["seeds"][1] ^ s["seeds"][3]
+
+
+def test_rng_is_not_textbook_mwc64x(oracle_sep):
+    """The reference adds 0xFFFFFFFF on carry; a textbook +1 MWC64X would give these out3 values instead."""
+    wrong = {((1, 2, 3, 4), 0): (0x1985e7ad, 0xe1858108), ((1, 2, 3, 4), 12345): (0xdd135ba1, 0x07877929),
+             ((123456789, 42, 7, 99999), 262143): (0x4b823e8a, 0x8e372978)}
+    right = {((1, 2, 3, 4), 0): (0x199a77e7, 0xe18030c6), ((1, 2, 3, 4), 12345): (0xdd135ba3, 0x07877929),
+             ((123456789, 42, 7, 99999), 262143): (0x4b9faed0, 0x89ca9932)}
+    for (seeds, gid), w in wrong.items():
+        _, u, _ = oracle_sep.rng_kat(seeds, gid, 4)
+        assert (int(u[6]), int(u[7])) == right[(seeds, gid)]
+        assert (int(u[6]), int(u[7])) != w
+
+
+def test_trace_ray_golden(oracle_sep, scene_dirs):
+    g = np.load(os.path.join(G, "golden_trace.npz"))
+    sc = oracle_sep.load_scene_dir(scene_dirs["lmem"], "lmem")
+    n = g["origins"].shape[0]
+    for variant, carry in (("base", 0), ("lmem", 1)):
+        bad = 0
+        for k in range(n):
+            m, t, nn = oracle_sep.trace_ray(carry, g["origins"][k], g["dirs"][k], float(g["t_in"][k]), sc["spheres"], sc["squares"], sc["triangles"])
+            ok = m == int(g["m_" + variant][k]) and np.float32(t).view(np.uint32) == g["t_" + variant][k]
+            if m:
+                ok = ok and np.array_equal(nn.view(np.uint32), g["n_" + variant][k])
+            bad += not ok
+        assert bad == 0, "%s: %d of %d rays differ from the reference TraceRay" % (variant, bad, n)
+    assert len(set(g["m_lmem"].tolist())) == 4    # the vectors cover sky, floor, diffuse and triangle hits
+
+
+@pytest.mark.parametrize("variant", ["base", "lmem", "nodof", "grid"])
+def test_image_rows_golden(oracle_sep, scene_dirs, variant):
+    g = np.load(os.path.join(G, "golden_images.npz"))
+    sc = oracle_sep.load_scene_dir(scene_dirs[variant], variant)
+    for si, seeds in enumerate(SEED_SETS):
+        for ri, row in enumerate(g["rows"]):
+            out = oracle_sep.render(variant, 512, 512, seeds, sc, rows=(int(row), int(row) + 1), want_rng=False)
+            assert np.array_equal(out["image"][row], g["%s_s%d_rows" % (variant, si)][ri]), (variant, si, int(row))
+
+
+def test_full_frame_hash_golden(oracle_sep, scene_dirs):
+    g = np.load(os.path.join(G, "golden_images.npz"))
+    sc = oracle_sep.load_scene_dir(scene_dirs["nodof"], "nodof")
+    out = oracle_sep.render("nodof", 512, 512, SEED_SETS[0], sc, want_rng=False, want_accum=False)
+    assert hashlib.sha256(out["image"].tobytes()).digest() == g["nodof_s0_sha256"].tobytes()
+    sc = oracle_sep.load_scene_dir(scene_dirs["torus"], "base")
+    out = oracle_sep.render("base", 640, 360, SEED_SETS[0], sc, want_rng=False, want_accum=False)
+    assert hashlib.sha256(out["image"].tobytes()).digest() == g["torus_640x360_sha256"].tobytes()
+
+
+def test_grid_with_other_mesh_and_modifier_golden(oracle_sep, tmp_path):
+    import write_scenes
+    g = np.load(os.path.join(G, "golden_images.npz"))
+    d = str(tmp_path / "gt")
+    write_scenes.write_variant("grid", d, mesh="torus")
+    sc = oracle_sep.load_scene_dir(d, "grid")
+    for ri, row in enumerate(g["rows"]):
+        out = oracle_sep.render("grid", 512, 512, SEED_SETS[0], sc, rows=(int(row), int(row) + 1), want_rng=False, modifier=6.5)
+        assert np.array_equal(out["image"][row], g["gridtorus_m6.5_rows"][ri])
+
+
+def test_grid_build_golden(oracle_sep, tmp_path):
+    import write_scenes
+    g = np.load(os.path.join(G, "golden_grid.npz"))
+    for name, mesh in (("default", None), ("torus", "torus"), ("torus_fine", "torus")):
+        d = str(tmp_path / name)
+        write_scenes.write_variant("grid", d, mesh=mesh)
+        sc = oracle_sep.load_scene_dir(d, "grid")
+        res, cell = oracle_sep.grid_dims(sc["box_min"], sc["box_max"], sc["triangles"].shape[0], float(g[name + "_modifier"]))
+        assert np.array_equal(res, g[name + "_res"]) and np.array_equal(cell.view(np.uint32), g[name + "_cell"])
+        start, refs = oracle_sep.build_grid(sc["triangles"], sc["box_min"], res, cell)
+        nels = g[name + "_nels"]
+        for c in range(len(nels)):
+            mine = refs[start[c]:start[c + 1]]
+            if nels[c] <= 62:      # below the cap the reference's (unordered) cell holds exactly this set
+                assert np.array_equal(np.sort(mine), g[name + "_ids"][c][: nels[c]].astype(np.uint32)), (name, c)
+            else:                  # reference overflows (bug); ours keeps the first 62 by triangle id
+                assert len(mine) == 62
+            assert np.all(np.diff(mine.astype(np.int64)) > 0)   # triangle-id order
+
+
+def test_host_golden(oracle_sep, scene_dirs):
+    g = json.load(open(os.path.join(G, "golden_host.json")))
+    cam = oracle_sep.camera()
+    line = "Cam_forward %f %f %f\nCam_up %f %f %f\nCam_right %f %f %f\n eye_offset %f %f %f" % (
+        *cam["cam_forward"][:3], *cam["cam_up"][:3], *cam["cam_right"][:3], *cam["eye_offset"][:3])
+    assert line == g["base"]["camera_print"]
+    # hex constants of SURVEY.md appendix B
+    assert [float(x).hex() for x in cam["cam_up"][:2]] == ["-0x1.eae7fc0000000p-10", "0x1.702dfe0000000p-11"]
+    assert [float(x).hex() for x in cam["eye_offset"][:3]] == ["0x1.06b6280000000p-3", "-0x1.1db9040000000p+0", "0x1.0624de0000000p-1"]
+    for v in ("base", "lmem", "nodof", "grid"):
+        sc = oracle_sep.load_scene_dir(scene_dirs[v], v)
+        assert sc["triangles"].shape[0] == g[v]["ntriangles"] and sc["lights"].shape[0] == g[v]["nlights"]
+    sc = oracle_sep.load_scene_dir(scene_dirs["grid"], "grid")
+    assert "vmax: %f %f %f, vmin: %f %f %f" % (*sc["box_max"][:3], *sc["box_min"][:3]) == g["grid"]["bbox_print"]
+    res, _ = oracle_sep.grid_dims(sc["box_min"], sc["box_max"], 96, 3.0)
+    assert list(res[:3]) == g["grid"]["grid_size"] == [8, 5, 6]
+    sc = oracle_sep.load_scene_dir(scene_dirs["torus"], "base")
+    assert sc["triangles"].shape[0] == g["torus"]["ntriangles"] == 32
+
+
+def test_contract_modes_agree_within_tolerance(oracle_sep, oracle_fma, scene_dirs):
+    """The two legal arithmetic policies: identical RNG streams on almost every pixel, images within 1 LSB."""
+    sc = oracle_sep.load_scene_dir(scene_dirs["lmem"], "lmem")
+    rows = (330, 362)
+    a = oracle_sep.render("lmem", 512, 512, SEED_SETS[0], sc, rows=rows)
+    b = oracle_fma.render("lmem", 512, 512, SEED_SETS[0], sc, rows=rows)
+    same_rng = (a["rng_state"] == b["rng_state"]).all(axis=1).reshape(512, 512)[rows[0]:rows[1]]
+    assert same_rng.mean() >= 0.999
+    diff = np.abs(a["image"][rows[0]:rows[1]].astype(int) - b["image"][rows[0]:rows[1]].astype(int))
+    assert (diff <= 1).mean() >= 0.995 and np.sqrt((diff.astype(float) ** 2).mean()) <= 0.5
+    rel = np.abs(a["accum"] - b["accum"])[rows[0]:rows[1]][same_rng] / np.maximum(np.abs(a["accum"][rows[0]:rows[1]][same_rng]), 1e-6)
+    assert np.median(rel) <= 1e-6
