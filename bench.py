@@ -329,7 +329,7 @@ def bench_ours(args, w, wname):
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wname, "description": w["desc"], "width": W, "height": H, "spp": spp, "seeds": list(SEEDS),
-                       "kernel": args.kernel, "scene_mem": args.scene_mem or ("const" if w["variant"] == "base" else "smem"),
+                       "kernel": args.kernel, "scene_mem": args.scene_mem or "auto",
                        "arith": "fma (bit-exact vs oracle -DPT_CONTRACT=1)", "l2": "flushed between timed steps (256 MiB write)",
                        "sharding": "8-row stripes round-robin over ranks + one NCCL reduce of the float accumulation buffer"
                        if world > 1 else "single GPU"},
@@ -370,8 +370,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
-    ap.add_argument("--kernel", default="mega", choices=["mega", "persistent", "wavefront"])
-    ap.add_argument("--scene-mem", default=None, choices=["const", "smem"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "mega", "persistent", "wavefront"])
+    ap.add_argument("--scene-mem", default=None, choices=["auto", "const", "smem"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]

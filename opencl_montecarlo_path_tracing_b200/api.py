@@ -124,7 +124,7 @@ class RenderResult:
     rng_state: np.ndarray = None      # (items, 4) uint32 if requested
 
 
-def make_params(variant, width, height, seeds, spp=64, kernel="mega", scene_mem=None, arith="fma", rows=None,
+def make_params(variant, width, height, seeds, spp=64, kernel="auto", scene_mem=None, arith="fma", rows=None,
                 want_accum=False, want_rng=False, interleave=0, rank=0, nranks=1):
     p = pt_render_params()
     p.variant = PT_VARIANT[variant]
@@ -134,7 +134,7 @@ def make_params(variant, width, height, seeds, spp=64, kernel="mega", scene_mem=
     p.seeds[:] = [int(s) & 0xFFFFFFFF for s in seeds]
     p.kernel = PT_KERNEL[kernel]
     if scene_mem is None:
-        scene_mem = "const" if variant == "base" else "smem"
+        scene_mem = "auto"
     p.scene_mem = PT_SCENE_MEM[scene_mem]
     p.arith = PT_ARITH[arith]
     p.want_accum, p.want_rng = int(bool(want_accum)), int(bool(want_rng))

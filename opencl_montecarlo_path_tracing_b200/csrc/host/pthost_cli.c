@@ -11,7 +11,7 @@
  * Extensions are env-only so the command line stays a drop-in:
  *   PT_SEEDS=a,b,c,d   fixed seeds (default: wall-clock recipe of the reference)
  *   PT_SPP=n           samples per pixel (default 64)
- *   PT_KERNEL=mega|persistent|wavefront     PT_SCENE_MEM=const|smem     PT_ARITH=fma|separate
+ *   PT_KERNEL=auto|mega|persistent|wavefront     PT_SCENE_MEM=auto|const|smem     PT_ARITH=fma|separate
  *   PT_MAX_TRIANGLES=n lift the 512 / 65536 MAX_TRIANGLES cap of the reference hosts
  *   PT_DEVICE / OCL_DEVICE   device index
  *   PT_STATS=1         append Mrays/s, samples/s and work counters after the reference's own lines
@@ -107,8 +107,8 @@ int pth_cli_main(int variant, int argc, char **argv) {
     pt_event grid_evt = NULL;
     if (grid) grid_evt = pt_build_grid(ctx, &gdesc);
 
-    static const char *const kernels[] = {"mega", "persistent", "wavefront"};
-    static const char *const mems[] = {"const", "smem"};
+    static const char *const kernels[] = {"mega", "persistent", "wavefront", "auto"};
+    static const char *const mems[] = {"const", "smem", "auto"};
     static const char *const ariths[] = {"separate", "fma"};
     pt_render_params rp;
     memset(&rp, 0, sizeof(rp));
@@ -117,8 +117,8 @@ int pth_cli_main(int variant, int argc, char **argv) {
     rp.height = img_height;
     rp.spp = getenv("PT_SPP") ? atoi(getenv("PT_SPP")) : 64;
     memcpy(rp.seeds, seeds, sizeof(seeds));
-    rp.kernel = env_choice("PT_KERNEL", kernels, 3, PT_KERNEL_MEGA);
-    rp.scene_mem = env_choice("PT_SCENE_MEM", mems, 2, variant == PT_VARIANT_BASE ? PT_SCENE_CONST : PT_SCENE_SMEM);
+    rp.kernel = env_choice("PT_KERNEL", kernels, 4, PT_KERNEL_AUTO);
+    rp.scene_mem = env_choice("PT_SCENE_MEM", mems, 3, PT_SCENE_AUTO);
     rp.arith = env_choice("PT_ARITH", ariths, 2, PT_ARITH_FMA);
 
     pt_event render_evt = pt_launch_pathtracer(ctx, &cam, &rp);

@@ -10,7 +10,7 @@
 //               reference's serial initTrianglesGrid_host (..._trianglegrid/CLSuperPathTracer.c:233-265)
 //               produces; the first `cap` (62) entries are kept,
 //   5. scan + emit : capped CSR (cell -> first record, count) and CONTIGUOUS per-cell triangle records
-//               (v0, e0, e2 as 3 x float4), so a traversal step reads one dense block instead of
+//               (e2, e0, v0 as 3 x float4), so a traversal step reads one dense block instead of
 //               chasing 16-bit indices into a triangle array.  32-bit ids: no 65536-triangle limit.
 #pragma once
 #include "pt_host.h"
@@ -162,9 +162,9 @@ __global__ void k_grid_emit(const float *__restrict__ tris, size_t ncells, uint3
         float4 *r = recs + 3 * (size_t)(first + k);
         float e0x = __fsub_rn(t[4], t[0]), e0y = __fsub_rn(t[5], t[1]), e0z = __fsub_rn(t[6], t[2]);
         float e2x = __fsub_rn(t[8], t[0]), e2y = __fsub_rn(t[9], t[1]), e2z = __fsub_rn(t[10], t[2]);
-        r[0] = make_float4(t[0], t[1], t[2], e0x);
-        r[1] = make_float4(e0y, e0z, e2x, e2y);
-        r[2] = make_float4(e2z, __uint_as_float(id), 0.f, 0.f);
+        r[0] = make_float4(e2x, e2y, e2z, e0x);
+        r[1] = make_float4(e0y, e0z, t[0], t[1]);
+        r[2] = make_float4(t[2], __uint_as_float(id), 0.f, 0.f);
     }
 }
 

@@ -234,9 +234,9 @@ extern "C" int pt_set_scene(pt_ctx c, const pt_scene *sc) {
             if (l0 * l2 < 0.005) continue;
             H3 e0 = {e0x, e0y, e0z}, e2 = {e2x, e2y, e2z};
             H3 n = h_normalize(fma, h_cross(fma, e0, e2));
-            S->tri[3 * kept + 0] = make_float4(t[0], t[1], t[2], e0.x);
-            S->tri[3 * kept + 1] = make_float4(e0.y, e0.z, e2.x, e2.y);
-            S->tri[3 * kept + 2] = make_float4(e2.z, n.x, n.y, n.z);
+            S->tri[3 * kept + 0] = make_float4(e2.x, e2.y, e2.z, e0.x);
+            S->tri[3 * kept + 1] = make_float4(e0.y, e0.z, t[0], t[1]);
+            S->tri[3 * kept + 2] = make_float4(t[2], n.x, n.y, n.z);
             ++kept;
         }
         S->ntri = kept;
@@ -418,7 +418,17 @@ static int fill_args(pt_ctx c, const pt_camera *cam, const pt_render_params *p, 
     return 0;
 }
 
-static int dispatch(pt_ctx c, const pt_render_params *p, const pt::LaunchArgs &A) {
+// PT_KERNEL_AUTO / PT_SCENE_AUTO: measured best per variant on B200
+static pt_render_params resolve_auto(const pt_render_params *in) {
+    pt_render_params p = *in;
+    if (p.kernel == PT_KERNEL_AUTO) p.kernel = p.variant == PT_VARIANT_GRID ? PT_KERNEL_MEGA : PT_KERNEL_PERSISTENT;
+    if (p.scene_mem == PT_SCENE_AUTO) p.scene_mem = p.variant == PT_VARIANT_NODOF ? PT_SCENE_CONST : PT_SCENE_SMEM;
+    return p;
+}
+
+static int dispatch(pt_ctx c, const pt_render_params *pin, const pt::LaunchArgs &A) {
+    const pt_render_params resolved = resolve_auto(pin);
+    const pt_render_params *p = &resolved;
     PT_CUDA(cudaMemsetAsync(c->d_counters, 0, 8 * sizeof(unsigned long long), c->stream), "clear counters");
     if (A.nrows <= 0) return 0;
     switch (p->kernel) {

@@ -14,7 +14,8 @@ from conftest import SEED_SETS
 pytestmark = pytest.mark.gpu
 
 # row windows of the 512x512 default view that contain every kind of content
-WINDOWS = {"sky+mesh+sphere": (96, 128), "horizon": (236, 268), "floor+sphere+shadow": (340, 372), "bottom": (496, 512)}
+WINDOWS = {"sky+mesh+sphere+square": (112, 144), "far squares+horizon": (196, 260), "floor+sphere+shadow": (340, 372),
+           "bottom": (496, 512)}
 
 
 def _oracle_scene(o, d, variant):
@@ -77,6 +78,20 @@ def test_scene_mem_and_seeds(renderer, scene_dirs, oracle_fma, variant):
             res = renderer.render(variant, W, H, SEED_SETS[1], rows=rows, scene_mem=mem, kernel=kernel, want_accum=True)
             assert np.array_equal(res.image[rows[0]:rows[1]], ref["image"][rows[0]:rows[1]]), (kernel, mem)
             assert np.array_equal(res.accum[rows[0]:rows[1]].view(np.uint32), ref["accum"][rows[0]:rows[1]].view(np.uint32)), (kernel, mem)
+
+
+@pytest.mark.parametrize("variant", ["base", "lmem", "nodof", "grid"])
+def test_full_frame_bit_exact(renderer, scene_dirs, oracle_fma, variant):
+    """Whole 512x512x64 default frame of every variant (default kernel choice): image, accumulation buffer,
+    RNG state of every work-item and all work counters equal the oracle's."""
+    d = scene_dirs[variant]
+    scene = pt.load_scene_dir(d, variant)
+    renderer.set_scene(scene)
+    if variant == "grid":
+        renderer.build_grid(pt.grid_dims(scene))
+    res = renderer.render(variant, 512, 512, SEED_SETS[1], want_accum=True, want_rng=True)
+    ref = oracle_fma.render(variant, 512, 512, SEED_SETS[1], _oracle_scene(oracle_fma, d, variant))
+    _compare(res, ref, "%s/full frame" % variant)
 
 
 def test_torus_mesh_and_spp_extension(renderer, scene_dirs, oracle_fma):
