@@ -64,6 +64,7 @@ class pt_render_params(C.Structure):
         ("row_interleave", C.c_int32),
         ("rank", C.c_int32),
         ("nranks", C.c_int32),
+        ("no_cull", C.c_int32),
     ]
 
 
@@ -75,6 +76,7 @@ class pt_counters(C.Structure):
         ("tri_tests", C.c_uint64),
         ("cells_visited", C.c_uint64),
         ("prim_tests", C.c_uint64),
+        ("tri_tests_executed", C.c_uint64),
     ]
 
     def as_dict(self):

@@ -125,7 +125,7 @@ class RenderResult:
 
 
 def make_params(variant, width, height, seeds, spp=64, kernel="auto", scene_mem=None, arith="fma", rows=None,
-                want_accum=False, want_rng=False, interleave=0, rank=0, nranks=1):
+                want_accum=False, want_rng=False, interleave=0, rank=0, nranks=1, cull=True):
     p = pt_render_params()
     p.variant = PT_VARIANT[variant]
     p.width, p.height, p.spp = int(width), int(height), int(spp)
@@ -139,6 +139,7 @@ def make_params(variant, width, height, seeds, spp=64, kernel="auto", scene_mem=
     p.arith = PT_ARITH[arith]
     p.want_accum, p.want_rng = int(bool(want_accum)), int(bool(want_rng))
     p.row_interleave, p.rank, p.nranks = int(interleave), int(rank), int(nranks)
+    p.no_cull = 0 if cull else 1
     return p
 
 

@@ -12,6 +12,8 @@
  *   PT_SEEDS=a,b,c,d   fixed seeds (default: wall-clock recipe of the reference)
  *   PT_SPP=n           samples per pixel (default 64)
  *   PT_KERNEL=auto|mega|persistent|wavefront     PT_SCENE_MEM=auto|const|smem     PT_ARITH=fma|separate
+ *   PT_NO_CULL=1       run the full brute-force triangle loop for every ray (default: rays whose line misses
+ *                      the mesh's bounding sphere skip it; identical results)
  *   PT_MAX_TRIANGLES=n lift the 512 / 65536 MAX_TRIANGLES cap of the reference hosts
  *   PT_DEVICE / OCL_DEVICE   device index
  *   PT_STATS=1         append Mrays/s, samples/s and work counters after the reference's own lines
@@ -120,6 +122,7 @@ int pth_cli_main(int variant, int argc, char **argv) {
     rp.kernel = env_choice("PT_KERNEL", kernels, 4, PT_KERNEL_AUTO);
     rp.scene_mem = env_choice("PT_SCENE_MEM", mems, 3, PT_SCENE_AUTO);
     rp.arith = env_choice("PT_ARITH", ariths, 2, PT_ARITH_FMA);
+    rp.no_cull = getenv("PT_NO_CULL") ? atoi(getenv("PT_NO_CULL")) : 0;
 
     pt_event render_evt = pt_launch_pathtracer(ctx, &cam, &rp);
     pt_event read_evt = NULL;

@@ -33,6 +33,7 @@ PT_DEV void flush_counters(const LaunchArgs &P, const Counters &c, int ntri_coun
     uint32_t cells = __reduce_add_sync(0xffffffffu, c.cells);
     uint32_t gtri = __reduce_add_sync(0xffffffffu, c.gtri);
     uint32_t samples = __reduce_add_sync(0xffffffffu, c.samples);
+    uint32_t loops = __reduce_add_sync(0xffffffffu, c.tri_loops);
     if ((threadIdx.x & 31) == 0 && P.counters) {
         atomicAdd(P.counters + 0, (unsigned long long)samples);
         atomicAdd(P.counters + 1, (unsigned long long)rays);
@@ -40,6 +41,7 @@ PT_DEV void flush_counters(const LaunchArgs &P, const Counters &c, int ntri_coun
         atomicAdd(P.counters + 3, (unsigned long long)gtri + (unsigned long long)rays * ntri_counted);
         atomicAdd(P.counters + 4, (unsigned long long)cells);
         atomicAdd(P.counters + 5, (unsigned long long)rays * nprims);
+        atomicAdd(P.counters + 6, (unsigned long long)gtri + (unsigned long long)loops * ntri_counted);
     }
 }
 
@@ -53,7 +55,7 @@ __global__ void __launch_bounds__(128) k_mega_pixel(const __grid_constant__ Laun
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
     const int vr = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
-    Counters cnt = {0, 0, 0, 0, 0};
+    Counters cnt = {0, 0, 0, 0, 0, 0};
     const int j = map_row(P, vr);
     if (i < P.W && vr < P.nrows && j < P.row_end) {
         Rng rng = rng_seed(P.seeds, (uint32_t)(j * P.W + i));
@@ -81,7 +83,7 @@ __global__ void __launch_bounds__(256) k_mega_nodof(const __grid_constant__ Laun
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int px = blockIdx.x * 4 + (warp & 3);
     const int vr = blockIdx.y * 2 + (warp >> 2);
-    Counters cnt = {0, 0, 0, 0, 0};
+    Counters cnt = {0, 0, 0, 0, 0, 0};
     const int py = map_row(P, vr);
     if (px < P.W && vr < P.nrows && py < P.row_end) {   // warp-uniform
         float ax[2], ay[2], az[2];

@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(128) k_sm_pixel(const __grid_constant__ Launch
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const SceneBlock *S = (MEM == PT_SCENE_SMEM) ? stage_scene_smem(P, smem_raw) : &c_scene;
     const unsigned lane = threadIdx.x & 31;
-    Counters cnt = {0, 0, 0, 0, 0};
+    Counters cnt = {0, 0, 0, 0, 0, 0};
     Lane L;
     L.phase = 0; L.l = 0; L.mat = 0; L.illum = 0.f; L.lam = 0.f; L.matf = 0.f; L.t = 1e9f;
     L.o = L.d = L.X = L.n = mk3(0.f, 0.f, 0.f);
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(256) k_sm_nodof(const __grid_constant__ Launch
     const SceneBlock *S = (MEM == PT_SCENE_SMEM) ? stage_scene_smem(P, smem_raw) : &c_scene;
     const int lane = threadIdx.x & 31;
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
-    Counters cnt = {0, 0, 0, 0, 0};
+    Counters cnt = {0, 0, 0, 0, 0, 0};
     const uint32_t tiles_x = (uint32_t)(P.W + 3) >> 2;    // pixels are walked in 4x2 tiles
     for (uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < npix_items; item += warps_total) {
         const uint32_t tile = item >> 3, pit = item & 7;

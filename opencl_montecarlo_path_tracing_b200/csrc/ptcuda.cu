@@ -242,6 +242,31 @@ extern "C" int pt_set_scene(pt_ctx c, const pt_scene *sc) {
         S->ntri = kept;
     }
     c->scene_bytes = (int)(offsetof(SceneBlock, tri) + (size_t)kept * 48);
+    {
+        // bounding sphere of the brute-force triangles' vertices (double precision), radius inflated by
+        // 1 % + 0.01 — far beyond any float rounding of the line/sphere test or of Moller-Trumbore
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        for (int i = 0; i < nbrute; ++i)
+            for (int v = 0; v < 3; ++v)
+                for (int a = 0; a < 3; ++a) {
+                    double x = sc->triangles[12 * (size_t)i + 4 * v + a];
+                    if (x < lo[a]) lo[a] = x;
+                    if (x > hi[a]) hi[a] = x;
+                }
+        double ctr[3] = {0, 0, 0}, r2 = 0;
+        if (nbrute > 0) for (int a = 0; a < 3; ++a) ctr[a] = 0.5 * (lo[a] + hi[a]);
+        for (int i = 0; i < nbrute; ++i)
+            for (int v = 0; v < 3; ++v) {
+                double dx = sc->triangles[12 * (size_t)i + 4 * v] - ctr[0], dy = sc->triangles[12 * (size_t)i + 4 * v + 1] - ctr[1],
+                       dz = sc->triangles[12 * (size_t)i + 4 * v + 2] - ctr[2];
+                double q = dx * dx + dy * dy + dz * dz;
+                if (q > r2) r2 = q;
+            }
+        double r = sqrt(r2) * 1.01 + 0.01;
+        for (int a = 0; a < 3; ++a) c->mesh_c[a] = (float)ctr[a];
+        c->mesh_r2 = (float)(r * r * 1.001 + 0.01);
+        if (!(c->mesh_r2 == c->mesh_r2) || !isfinite(c->mesh_r2)) c->mesh_r2 = INFINITY;
+    }
     for (int a = 0; a < 2; ++a)
         PT_CUDA(cudaMemcpyAsync(c->d_scene[a], c->h_scene[a], sizeof(SceneBlock), cudaMemcpyHostToDevice, c->stream),
                 "upload scene");
@@ -415,13 +440,15 @@ static int fill_args(pt_ctx c, const pt_camera *cam, const pt_render_params *p, 
     A->ap.nsq = hs->nsq; A->ap.nsp = hs->nsp; A->ap.nlights = hs->nlights;
     for (int i = 0; i < PT_FAST_PRIMS; ++i) { A->ap.sq[i] = hs->sq[i]; A->ap.sp[i] = hs->sp[i]; }
     for (int i = 0; i < 5; ++i) A->ap.lights[i] = hs->lights[i];
+    A->ap.mesh_cx = c->mesh_c[0]; A->ap.mesh_cy = c->mesh_c[1]; A->ap.mesh_cz = c->mesh_c[2];
+    A->ap.mesh_r2 = p->no_cull ? INFINITY : c->mesh_r2;
     return 0;
 }
 
 // PT_KERNEL_AUTO / PT_SCENE_AUTO: measured best per variant on B200
 static pt_render_params resolve_auto(const pt_render_params *in) {
     pt_render_params p = *in;
-    if (p.kernel == PT_KERNEL_AUTO) p.kernel = p.variant == PT_VARIANT_GRID ? PT_KERNEL_MEGA : PT_KERNEL_PERSISTENT;
+    if (p.kernel == PT_KERNEL_AUTO) p.kernel = p.variant == PT_VARIANT_NODOF ? PT_KERNEL_PERSISTENT : PT_KERNEL_MEGA;
     if (p.scene_mem == PT_SCENE_AUTO) p.scene_mem = p.variant == PT_VARIANT_NODOF ? PT_SCENE_CONST : PT_SCENE_SMEM;
     return p;
 }
@@ -518,7 +545,7 @@ extern "C" int pt_get_counters(pt_ctx c, pt_counters *out) {
     PT_CUDA(cudaMemcpyAsync(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream), "read counters");
     PT_CUDA(cudaStreamSynchronize(c->stream), "sync");
     out->samples = h[0]; out->rays = h[1]; out->shadow_rays = h[2]; out->tri_tests = h[3];
-    out->cells_visited = h[4]; out->prim_tests = h[5];
+    out->cells_visited = h[4]; out->prim_tests = h[5]; out->tri_tests_executed = h[6];
     return 0;
 }
 
@@ -538,7 +565,7 @@ __global__ void k_probe_trace(int variant, int n, const float *o, const float *d
     if (i >= n) return;
     V3 oo = mk3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), dd = mk3(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
     float tt = t[i];
-    Counters cnt = {0, 0, 0, 0, 0};
+    Counters cnt = {0, 0, 0, 0, 0, 0};
     int hit;
     V3 nn = mk3(0.f, 0.f, 0.f);
     if (variant == PT_VARIANT_BASE) {

@@ -36,8 +36,8 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.pt_scene) == 36 + 36 + 8 + 4 + 80 + 4 + 4 or C.sizeof(_lib.pt_scene) % 8 == 0
     assert C.sizeof(_lib.pt_camera) == 64
     assert C.sizeof(_lib.pt_grid) == 68
-    assert C.sizeof(_lib.pt_render_params) == 4 * 6 + 16 + 4 * 8
-    assert C.sizeof(_lib.pt_counters) == 48
+    assert C.sizeof(_lib.pt_render_params) == 4 * 6 + 16 + 4 * 9
+    assert C.sizeof(_lib.pt_counters) == 56
 
 
 @pytest.mark.skipif(_lib.cuda_lib().pt_device_count() > 0, reason="only meaningful without a GPU")

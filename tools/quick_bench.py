@@ -26,8 +26,8 @@ with pt.Renderer(0) as r, tempfile.TemporaryDirectory() as tmp:
                 spp = 64 if v == "nodof" else SPP
                 best = 1e9
                 for it in range(5):
-                    res = r.render(v, W, H, (1, 2, 3, 4), spp=spp, kernel=kernel, scene_mem=mem, read_image=False)
+                    res = r.render(v, W, H, (1, 2, 3, 4), spp=spp, kernel=kernel, scene_mem=mem, read_image=False, cull=os.environ.get("QB_CULL", "1") == "1")
                     best = min(best, res.ms)
                 c = res.counters
-                print("%-6s %-10s %-5s %4dx%-4d spp %-4d  %8.3f ms  %9.1f Mrays/s  %8.1f Msamples/s  rays %d" % (
-                    v, kernel, mem, W, H, spp, best, c["rays"] / 1e3 / best, c["samples"] / 1e3 / best, c["rays"]), flush=True)
+                print("%-6s %-10s %-5s %4dx%-4d spp %-4d  %8.3f ms  %9.1f Mrays/s  %8.1f Msamples/s  rays %d tri_exec %d" % (
+                    v, kernel, mem, W, H, spp, best, c["rays"] / 1e3 / best, c["samples"] / 1e3 / best, c["rays"], c["tri_tests_executed"]), flush=True)
