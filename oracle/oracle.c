@@ -346,10 +346,11 @@ int oracle_render(const oracle_job *J, uint8_t *rgba8, float *accum, uint32_t *r
         oracle_counters cnt;
         memset(&cnt, 0, sizeof(cnt));
 #ifdef _OPENMP
-#pragma omp for schedule(dynamic, 1)
+#pragma omp for schedule(dynamic, 64)
 #endif
-        for (int j = r0; j < r1; ++j) {
-            for (int i = 0; i < W; ++i) {
+        for (long lin = (long)r0 * W; lin < (long)r1 * W; ++lin) {
+            {
+                const int j = (int)(lin / W), i = (int)(lin - (long)j * W);
                 float col[4];
                 size_t pix = (size_t)j * W + i;
                 if (J->variant != ORACLE_NODOF) {

@@ -167,7 +167,11 @@ class OracleLib:
             if grid is None:
                 res, cell = self.grid_dims(scene["box_min"], scene["box_max"], tris.shape[0], modifier)
                 grid = {"box_min": scene["box_min"], "box_max": scene["box_max"], "res": res, "cell_size": cell}
-            start, refs = self.build_grid(tris, grid["box_min"], grid["res"], grid["cell_size"])
+            if "csr" in grid:
+                start, refs = grid["csr"]
+            else:
+                start, refs = self.build_grid(tris, grid["box_min"], grid["res"], grid["cell_size"])
+                grid["csr"] = (start, refs)          # callers that keep `grid` reuse the binning
             if refs.size == 0:
                 refs = np.zeros(1, np.uint32)
             keep = (start, refs)
