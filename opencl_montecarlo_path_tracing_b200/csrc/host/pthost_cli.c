@@ -109,7 +109,7 @@ int pth_cli_main(int variant, int argc, char **argv) {
     pt_event grid_evt = NULL;
     if (grid) grid_evt = pt_build_grid(ctx, &gdesc);
 
-    static const char *const kernels[] = {"mega", "persistent", "wavefront", "auto"};
+    static const char *const kernels[] = {"mega", "persistent", "wavefront", "auto", "grid_tma"};
     static const char *const mems[] = {"const", "smem", "auto"};
     static const char *const ariths[] = {"separate", "fma"};
     pt_render_params rp;
@@ -119,7 +119,7 @@ int pth_cli_main(int variant, int argc, char **argv) {
     rp.height = img_height;
     rp.spp = getenv("PT_SPP") ? atoi(getenv("PT_SPP")) : 64;
     memcpy(rp.seeds, seeds, sizeof(seeds));
-    rp.kernel = env_choice("PT_KERNEL", kernels, 4, PT_KERNEL_AUTO);
+    rp.kernel = env_choice("PT_KERNEL", kernels, 5, PT_KERNEL_AUTO);
     rp.scene_mem = env_choice("PT_SCENE_MEM", mems, 3, PT_SCENE_AUTO);
     rp.arith = env_choice("PT_ARITH", ariths, 2, PT_ARITH_FMA);
     rp.no_cull = getenv("PT_NO_CULL") ? atoi(getenv("PT_NO_CULL")) : 0;

@@ -106,4 +106,5 @@ int pt_bind_const_scene(pt_ctx ctx, int arith);
 int pt_launch_mega(pt_ctx ctx, const pt_render_params *p, const pt::LaunchArgs &args);
 int pt_launch_persistent(pt_ctx ctx, const pt_render_params *p, const pt::LaunchArgs &args);
 int pt_launch_wavefront(pt_ctx ctx, const pt_render_params *p, const pt::LaunchArgs &args);
+int pt_launch_grid_tma(pt_ctx ctx, const pt_render_params *p, const pt::LaunchArgs &args);
 int pt_grid_build_device(pt_ctx ctx, const pt_grid *g);

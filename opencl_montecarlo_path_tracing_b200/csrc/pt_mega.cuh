@@ -27,26 +27,34 @@ PT_DEV const SceneBlock *stage_scene_smem(const LaunchArgs &P, unsigned char *sm
     return reinterpret_cast<const SceneBlock *>(smem);
 }
 
+// Work counters: warp shuffle-reduce, then ONE set of global atomics per CTA (and none for zero sums) —
+// the wavefront kernels call this once per launch, so per-warp atomics on seven shared addresses would
+// serialise in L2.  Must be reached by every thread of the CTA.
 PT_DEV void flush_counters(const LaunchArgs &P, const Counters &c, int ntri_counted, int nprims) {
+    __shared__ unsigned long long s_cnt[7];
+    if (threadIdx.x < 7) s_cnt[threadIdx.x] = 0ull;
+    __syncthreads();
     uint32_t rays = __reduce_add_sync(0xffffffffu, c.rays);
     uint32_t shadow = __reduce_add_sync(0xffffffffu, c.shadow);
     uint32_t cells = __reduce_add_sync(0xffffffffu, c.cells);
     uint32_t gtri = __reduce_add_sync(0xffffffffu, c.gtri);
     uint32_t samples = __reduce_add_sync(0xffffffffu, c.samples);
     uint32_t loops = __reduce_add_sync(0xffffffffu, c.tri_loops);
-    if ((threadIdx.x & 31) == 0 && P.counters) {
-        atomicAdd(P.counters + 0, (unsigned long long)samples);
-        atomicAdd(P.counters + 1, (unsigned long long)rays);
-        atomicAdd(P.counters + 2, (unsigned long long)shadow);
-        atomicAdd(P.counters + 3, (unsigned long long)gtri + (unsigned long long)rays * ntri_counted);
-        atomicAdd(P.counters + 4, (unsigned long long)cells);
-        atomicAdd(P.counters + 5, (unsigned long long)rays * nprims);
-        atomicAdd(P.counters + 6, (unsigned long long)gtri + (unsigned long long)loops * ntri_counted);
+    if ((threadIdx.x & 31) == 0) {
+        if (samples) atomicAdd(&s_cnt[0], (unsigned long long)samples);
+        if (rays) atomicAdd(&s_cnt[1], (unsigned long long)rays);
+        if (shadow) atomicAdd(&s_cnt[2], (unsigned long long)shadow);
+        if (gtri | rays) atomicAdd(&s_cnt[3], (unsigned long long)gtri + (unsigned long long)rays * ntri_counted);
+        if (cells) atomicAdd(&s_cnt[4], (unsigned long long)cells);
+        if (rays) atomicAdd(&s_cnt[5], (unsigned long long)rays * nprims);
+        if (gtri | loops) atomicAdd(&s_cnt[6], (unsigned long long)gtri + (unsigned long long)loops * ntri_counted);
     }
+    __syncthreads();
+    if (threadIdx.x < 7 && P.counters && s_cnt[threadIdx.x]) atomicAdd(P.counters + threadIdx.x, s_cnt[threadIdx.x]);
 }
 
 template <int VARIANT, bool FMA, int MEM>
-__global__ void __launch_bounds__(128) k_mega_pixel(const __grid_constant__ LaunchArgs P) {
+__global__ void __launch_bounds__(128, VARIANT == PT_VARIANT_GRID ? 6 : 8) k_mega_pixel(const __grid_constant__ LaunchArgs P) {
     constexpr bool CARRY = VARIANT != PT_VARIANT_BASE;
     constexpr bool GRID = VARIANT == PT_VARIANT_GRID;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -77,7 +85,7 @@ __global__ void __launch_bounds__(128) k_mega_pixel(const __grid_constant__ Laun
 }
 
 template <bool FMA, int MEM>
-__global__ void __launch_bounds__(256) k_mega_nodof(const __grid_constant__ LaunchArgs P) {
+__global__ void __launch_bounds__(256, 4) k_mega_nodof(const __grid_constant__ LaunchArgs P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const SceneBlock *S = (MEM == PT_SCENE_SMEM) ? stage_scene_smem(P, smem_raw) : &c_scene;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

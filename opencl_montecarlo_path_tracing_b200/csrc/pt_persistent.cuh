@@ -112,7 +112,7 @@ PT_DEV bool item_to_pixel(const LaunchArgs &P, uint32_t w, int &i, int &j) {
 }
 
 template <int VARIANT, bool FMA, int MEM, bool REGEN>
-__global__ void __launch_bounds__(128) k_sm_pixel(const __grid_constant__ LaunchArgs P, uint32_t nitems, uint32_t *work_counter) {
+__global__ void __launch_bounds__(128, VARIANT == PT_VARIANT_GRID ? 6 : 8) k_sm_pixel(const __grid_constant__ LaunchArgs P, uint32_t nitems, uint32_t *work_counter) {
     constexpr bool CARRY = VARIANT != PT_VARIANT_BASE;
     constexpr bool GRID = VARIANT == PT_VARIANT_GRID;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(128) k_sm_pixel(const __grid_constant__ Launch
 // NoDoF: one warp per pixel (the 8x8 reduction tree lives in one warp), lanes run their two samples
 // through the state machine; warps are persistent and stride over the pixels.
 template <bool FMA, int MEM>
-__global__ void __launch_bounds__(256) k_sm_nodof(const __grid_constant__ LaunchArgs P, uint32_t npix_items) {
+__global__ void __launch_bounds__(256, 4) k_sm_nodof(const __grid_constant__ LaunchArgs P, uint32_t npix_items) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const SceneBlock *S = (MEM == PT_SCENE_SMEM) ? stage_scene_smem(P, smem_raw) : &c_scene;
     const int lane = threadIdx.x & 31;

@@ -16,6 +16,7 @@
 #include "pt_persistent.cuh"
 #include "pt_wavefront.cuh"
 #include "pt_gridbuild.cuh"
+#include "pt_gridtma.cuh"
 
 // ------------------------------------------------------------------------------------ errors
 static int g_error_mode = PT_ERRORS_EXIT;
@@ -462,6 +463,7 @@ static int dispatch(pt_ctx c, const pt_render_params *pin, const pt::LaunchArgs 
         case PT_KERNEL_MEGA: return pt_launch_mega(c, p, A);
         case PT_KERNEL_PERSISTENT: return pt_launch_persistent(c, p, A);
         case PT_KERNEL_WAVEFRONT: return pt_launch_wavefront(c, p, A);
+        case PT_KERNEL_GRID_TMA: return pt_launch_grid_tma(c, p, A);
     }
     return pt_fail(1, "render: unknown kernel kind %d", p->kernel);
 }

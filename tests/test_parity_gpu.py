@@ -36,7 +36,7 @@ def _compare(res, ref, what):
 
 @pytest.mark.parametrize("variant", ["base", "lmem", "nodof", "grid"])
 @pytest.mark.parametrize("arith", ["fma", "separate"])
-@pytest.mark.parametrize("kernel", ["mega", "persistent"])
+@pytest.mark.parametrize("kernel", ["mega", "persistent", "wavefront"])
 def test_bit_exact_windows(renderer, scene_dirs, oracle_fma, oracle_sep, variant, arith, kernel):
     o = oracle_fma if arith == "fma" else oracle_sep
     d = scene_dirs[variant]
@@ -148,7 +148,8 @@ def _soup_scene(n, seed, box):
     return base, osc
 
 
-@pytest.mark.parametrize("n,box,kernel", [(30000, 24.0, "mega"), (30000, 24.0, "persistent"), (70000, 30.0, "mega")])
+@pytest.mark.parametrize("n,box,kernel", [(30000, 24.0, "mega"), (30000, 24.0, "persistent"), (30000, 24.0, "wavefront"),
+                                          (30000, 24.0, "grid_tma"), (70000, 30.0, "mega")])
 def test_grid_synthetic_soup_bit_exact(renderer, oracle_fma, n, box, kernel):
     """Uniform-grid traversal on a seeded triangle soup (the config-4/5 generator at test size); 70000
     triangles exceed the reference's 16-bit cell ids (wide ids).  The camera sits inside the box."""
@@ -169,6 +170,26 @@ def test_grid_synthetic_soup_bit_exact(renderer, oracle_fma, n, box, kernel):
     res.image, ref["image"] = res.image[r0:r1], ref["image"][r0:r1]
     _compare(res, ref, "grid soup %d %s" % (n, kernel))
     assert res.counters["cells_visited"] > 0 and res.counters["tri_tests"] > 0
+
+
+def test_grid_tma_default_scene_and_dense_cells(renderer, scene_dirs, oracle_fma):
+    """TMA-staged warp-per-ray traversal: default grid scene, and CELL_SIZE_MODIFIER 0.02 (one fat cell capped at 62)."""
+    d = scene_dirs["grid"]
+    scene = pt.load_scene_dir(d, "grid")
+    renderer.set_scene(scene)
+    osc = _oracle_scene(oracle_fma, d, "grid")
+    W = H = 512
+    for mod, rows in ((3.0, (112, 144)), (0.02, (120, 136))):
+        g = pt.grid_dims(scene, mod)
+        renderer.build_grid(g)
+        res = renderer.render("grid", W, H, SEED_SETS[0], rows=rows, kernel="grid_tma", want_accum=True, want_rng=True)
+        ref = oracle_fma.render("grid", W, H, SEED_SETS[0], osc, rows=rows, modifier=mod, grid=None)
+        r0, r1 = rows
+        assert np.array_equal(res.image[r0:r1], ref["image"][r0:r1]), mod
+        assert np.array_equal(res.accum[r0:r1].view(np.uint32), ref["accum"][r0:r1].view(np.uint32)), mod
+        assert np.array_equal(res.rng_state.reshape(H, W, 4)[r0:r1], ref["rng_state"].reshape(H, W, 4)[r0:r1]), mod
+        for k in ("rays", "shadow_rays", "cells_visited", "tri_tests"):
+            assert res.counters[k] == ref["counters"][k], (mod, k)
 
 
 def test_grid_build_matches_reference_cells(renderer, scene_dirs):

@@ -22,7 +22,7 @@ with pt.Renderer(0) as r, tempfile.TemporaryDirectory() as tmp:
         if v == "grid":
             r.build_grid(pt.grid_dims(scene))
         for kernel in os.environ.get("QB_KERNELS", "mega,persistent").split(","):
-            for mem in ("const", "smem"):
+            for mem in (("const",) if kernel == "wavefront" else ("const", "smem")):
                 spp = 64 if v == "nodof" else SPP
                 best = 1e9
                 for it in range(5):

@@ -21,10 +21,10 @@ scene = pt.Scene(np.array([1024, 0, 0, 0, 145, 0, 0, 2048, 0], np.int32), np.arr
                  tris, np.array([[10, 4, 10, 400], [15, 2, 7, 300]], np.float32), lo, hi)
 with pt.Renderer(0) as r:
     t0 = time.time(); r.set_scene(scene); t1 = time.time()
-    g = pt.grid_dims(scene)
+    g = pt.grid_dims(scene, float(os.environ.get("QG_MOD", "3.0")))
     ms = r.build_grid(g)
     print("set_scene %.1f ms, grid %dx%dx%d built in %.2f ms (device)" % ((t1 - t0) * 1e3, g.res[0], g.res[1], g.res[2], ms), flush=True)
-    for kernel in os.environ.get("QG_KERNELS", "mega,persistent").split(","):
+    for kernel in os.environ.get("QG_KERNELS", "mega,persistent,grid_tma").split(","):
         best = 1e9
         for it in range(3):
             res = r.render("grid", W, H, (1, 2, 3, 4), spp=spp, kernel=kernel, read_image=False)
