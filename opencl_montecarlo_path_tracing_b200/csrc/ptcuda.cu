@@ -436,7 +436,7 @@ static int fill_args(pt_ctx c, const pt_camera *cam, const pt_render_params *p, 
     A->grid = c->grid;
     const int arith = p->arith != PT_ARITH_SEPARATE ? PT_ARITH_FMA : PT_ARITH_SEPARATE;
     A->gscene = c->d_scene[arith];
-    A->scene_bytes = c->scene_bytes;
+    A->scene_bytes = p->variant == PT_VARIANT_GRID ? (int)offsetof(pt::SceneBlock, tri) : c->scene_bytes;  // grid: no brute-force records
     const pt::SceneBlock *hs = c->h_scene[arith];
     A->ap.nsq = hs->nsq; A->ap.nsp = hs->nsp; A->ap.nlights = hs->nlights;
     for (int i = 0; i < PT_FAST_PRIMS; ++i) { A->ap.sq[i] = hs->sq[i]; A->ap.sp[i] = hs->sp[i]; }
@@ -450,7 +450,8 @@ static int fill_args(pt_ctx c, const pt_camera *cam, const pt_render_params *p, 
 static pt_render_params resolve_auto(const pt_render_params *in) {
     pt_render_params p = *in;
     if (p.kernel == PT_KERNEL_AUTO) p.kernel = p.variant == PT_VARIANT_NODOF ? PT_KERNEL_PERSISTENT : PT_KERNEL_MEGA;
-    if (p.scene_mem == PT_SCENE_AUTO) p.scene_mem = p.variant == PT_VARIANT_NODOF ? PT_SCENE_CONST : PT_SCENE_SMEM;
+    if (p.scene_mem == PT_SCENE_AUTO)
+        p.scene_mem = (p.variant == PT_VARIANT_NODOF || p.variant == PT_VARIANT_GRID) ? PT_SCENE_CONST : PT_SCENE_SMEM;
     return p;
 }
 

@@ -208,3 +208,21 @@ def test_grid_build_matches_reference_cells(renderer, scene_dirs):
         assert np.array_equal(nels, np.minimum(gn, 62))
         for c in np.nonzero(gn <= 62)[0]:
             assert np.array_equal(ids[c, :gn[c]], g[name + "_ids"][c][:gn[c]])
+
+
+@pytest.mark.parametrize("kernel", ["mega", "persistent", "wavefront"])
+def test_many_analytic_primitives(renderer, scene_dirs, oracle_fma, kernel):
+    """More than 8 spheres / squares leaves the parameter-resident fast path (lists in the scene block)."""
+    scene = pt.load_scene_dir(scene_dirs["lmem"], "lmem")
+    scene.spheres = np.array([1024 + 64 + 4, 2, 0, 16384, 145, 0, 8 + 512, 2048, 65536], np.int32)      # 12 spheres
+    scene.squares = np.array([4096, 1, 32, 0, 2 + 1024, 0, 129, 16, 8192 + 8], np.int32)               # 10 squares
+    renderer.set_scene(scene)
+    osc = {"spheres": scene.spheres, "squares": scene.squares, "triangles": scene.triangles, "lights": scene.lights}
+    W = H = 512
+    for rows in ((120, 136), (340, 356)):
+        res = renderer.render("lmem", W, H, SEED_SETS[0], rows=rows, kernel=kernel, want_accum=True, want_rng=True)
+        ref = oracle_fma.render("lmem", W, H, SEED_SETS[0], osc, rows=rows)
+        r0, r1 = rows
+        assert np.array_equal(res.accum[r0:r1].view(np.uint32), ref["accum"][r0:r1].view(np.uint32))
+        assert np.array_equal(res.rng_state.reshape(H, W, 4)[r0:r1], ref["rng_state"].reshape(H, W, 4)[r0:r1])
+        assert res.counters["prim_tests"] == ref["counters"]["prim_tests"]
