@@ -230,6 +230,27 @@ def cpu_reference_measure(w, d, H):
                 sample="oracle port, rows %s of the %dx%d frame at %d spp (work is linear in rows and spp)" % (rows, w["W"], H, spp))
 
 
+def reference_opencl_on_gpu(w, d, H, rays):
+    """The unmodified reference run by NVIDIA's OpenCL runtime on this GPU (oracle/_ref/ocl, if built and the
+    ICD is usable): the "same kernel, same box" baseline.  Returns a dict or None."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ocl", w["variant"], "CLSuperPathTracer")
+    if not os.path.exists(exe) or is_heavy(w):
+        return None
+    env = dict(os.environ, OCL_ICD_FILENAMES="libnvidia-opencl.so.1", PT_SEEDS=",".join(str(s) for s in SEEDS))
+    best = None
+    try:
+        for _ in range(3):
+            p = subprocess.run([exe, str(w["W"]), str(H)], cwd=d, env=env, capture_output=True, text=True, timeout=300)
+            if p.returncode != 0:
+                return None
+            ms = sum(float(x) for x in re.findall(r"(?:rendering|reduce img samples) : .*? in ([0-9.eE+-]+)ms", p.stdout))
+            best = ms if best is None else min(best, ms)
+    except Exception:
+        return None
+    return {"value": rays / 1e3 / best, "unit": "Mrays/s", "kernel_ms": best,
+            "what": "unmodified reference .c + .ocl, NVIDIA OpenCL ICD on the same B200, OpenCL event time, best of 3"}
+
+
 def reference_rays(w, d, H):
     """Ray count of the frame (same seeds) from the oracle's counters, to turn reference times into Mrays/s."""
     from oracle import pyoracle
@@ -434,8 +455,11 @@ def bench_ours(args, w, wname):
                         import shutil
                         shutil.copy(os.path.join(d2, "squares.txt"), os.path.join(d2, "planes.txt"))
                     m = cpu_reference_measure(w, d2, H)
+                    ocl = reference_opencl_on_gpu(w, d2, H, rays)
                 line["cpu_baseline"] = {"value": m["mrays"], "unit": "Mrays/s", "cores": m["cores"], "kind": m["kind"],
                                         "ms": m["ms"], "sample": m["sample"]}
+                if ocl:
+                    line["reference_opencl_same_gpu"] = ocl
             except Exception as exc:  # pragma: no cover - reporting only
                 line["cpu_baseline"] = {"error": str(exc)}
         print(json.dumps(line))

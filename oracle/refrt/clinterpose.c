@@ -1,0 +1,48 @@
+/*
+ * clinterpose.c — TEST INFRASTRUCTURE ONLY.  Linked into oracle/_ref/ocl/<variant>/CLSuperPathTracer, the
+ * UNMODIFIED reference host program built against a REAL OpenCL runtime (NVIDIA's ICD on the B200 box:
+ * OCL_ICD_FILENAMES=libnvidia-opencl.so.1).  Two entry points are interposed, nothing else:
+ *   clCreateProgramWithSource : the reference passes the one-line source `#include "pathtracer.ocl"`
+ *       (ocl_boiler.h:176) and expects the file in the CWD; /root/reference does not exist on the GPU box,
+ *       so the kernel text — embedded into this binary at build time, never stored in the repo — is handed
+ *       to the runtime instead;
+ *   clSetKernelArg : PT_SEEDS=a,b,c,d replaces the wall-clock seeds (CLSuperPathTracer.c:209) so that runs
+ *       are reproducible and comparable with the oracle / CUDA path.
+ */
+#define _GNU_SOURCE
+#include <CL/cl.h>
+#include <dlfcn.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+extern const unsigned char ref_kernel_source[];
+extern const unsigned int ref_kernel_source_len;
+#ifndef SEEDS_ARG
+#error "SEEDS_ARG must be defined"
+#endif
+
+cl_program clCreateProgramWithSource(cl_context ctx, cl_uint count, const char **strings, const size_t *lengths, cl_int *err) {
+    typedef cl_program (*fn_t)(cl_context, cl_uint, const char **, const size_t *, cl_int *);
+    static fn_t real;
+    if (!real) real = (fn_t)dlsym(RTLD_NEXT, "clCreateProgramWithSource");
+    (void)count; (void)strings; (void)lengths;
+    const char *src = (const char *)ref_kernel_source;
+    size_t len = ref_kernel_source_len;
+    return real(ctx, 1, &src, &len, err);
+}
+
+cl_int clSetKernelArg(cl_kernel k, cl_uint idx, size_t size, const void *value) {
+    typedef cl_int (*fn_t)(cl_kernel, cl_uint, size_t, const void *);
+    static fn_t real;
+    if (!real) real = (fn_t)dlsym(RTLD_NEXT, "clSetKernelArg");
+    const char *env = getenv("PT_SEEDS");
+    if (env && value && idx == SEEDS_ARG && size == 16) {
+        unsigned long v[4];
+        if (sscanf(env, "%lu,%lu,%lu,%lu", &v[0], &v[1], &v[2], &v[3]) == 4) {
+            cl_uint s[4] = {(cl_uint)v[0], (cl_uint)v[1], (cl_uint)v[2], (cl_uint)v[3]};
+            return real(k, idx, size, s);
+        }
+    }
+    return real(k, idx, size, value);
+}

@@ -8,8 +8,8 @@
  *   REF_VARIANT 2  CLSuperPathTracer_lmem_NoDoF/pathtracer.ocl   (nodof)
  *   REF_VARIANT 3  CLSuperPathTracer_trianglegrid/pathtracer.ocl (grid)
  *
- * The generated file is the reference source with vector literals rewritten
- * by ocl2cpp.py; it lives under oracle/_ref/gen (git-ignored).  Argument
+ * REF_OCL_GEN is the reference source with vector literals rewritten by ocl2cpp.py; the Makefile
+ * pipes it in ("/dev/stdin"), so no copy of it is written anywhere.  Argument
  * indices below follow the clSetKernelArg sequences of the reference hosts:
  *   base  CLSuperPathTracer/CLSuperPathTracer.c:153-177
  *   lmem  CLSuperPathTracer_lmem/CLSuperPathTracer.c:154-186
