@@ -24,6 +24,7 @@ struct LaunchArgs {
     AnalyticParams ap;             // floor/squares/spheres/lights in kernel-parameter space
     const SceneBlock *gscene;      // global-memory copy of the scene block (shared-memory staging source)
     int scene_bytes;               // bytes of the block actually used (header + prims + ntri records)
+    uint32_t scatter_mul;          // persistent kernel: work item w -> (w * scatter_mul) % nitems (0 = identity)
 };
 
 // virtual row -> image row (identity, or the rank's interleaved stripes)

@@ -54,7 +54,7 @@ PT_DEV void flush_counters(const LaunchArgs &P, const Counters &c, int ntri_coun
 }
 
 template <int VARIANT, bool FMA, int MEM>
-__global__ void __launch_bounds__(128, VARIANT == PT_VARIANT_GRID ? 6 : 8) k_mega_pixel(const __grid_constant__ LaunchArgs P) {
+__global__ void __launch_bounds__(128, 6) k_mega_pixel(const __grid_constant__ LaunchArgs P) {
     constexpr bool CARRY = VARIANT != PT_VARIANT_BASE;
     constexpr bool GRID = VARIANT == PT_VARIANT_GRID;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -126,7 +126,9 @@ __global__ void __launch_bounds__(256, 4) k_mega_nodof(const __grid_constant__ L
 }
 
 template <int VARIANT, bool FMA, int MEM>
-static int launch_pixel(pt_ctx ctx, const LaunchArgs &args) {
+static int launch_pixel(pt_ctx ctx, const LaunchArgs &args_in) {
+    LaunchArgs args = args_in;
+    args.ap.tri_coop = MEM == PT_SCENE_SMEM;
     dim3 grid((args.W + 15) / 16, (args.nrows + 7) / 8), block(128);
     size_t smem = MEM == PT_SCENE_SMEM ? (size_t)args.scene_bytes : 0;
     if (smem > 48 * 1024)

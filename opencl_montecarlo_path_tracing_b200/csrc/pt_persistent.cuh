@@ -12,6 +12,8 @@
 // Bit-exactness is untouched: each pixel still consumes its own RNG stream in order;
 // only the interleaving of independent pixels on a lane changes.
 #pragma once
+#include <numeric>
+
 #include "pt_host.h"
 
 namespace pt {
@@ -101,7 +103,12 @@ PT_DEV bool lane_step(const LaunchArgs &P, const SceneBlock *S, Lane &L, bool ac
 
 // work item -> pixel: items are numbered tile-major over 8x4 pixel tiles so that the 32 items a warp
 // holds at any time stay spatially close (coherent rays) even after regeneration.
-PT_DEV bool item_to_pixel(const LaunchArgs &P, uint32_t w, int &i, int &j) {
+PT_DEV bool item_to_pixel(const LaunchArgs &P, uint32_t w, int &i, int &j, uint32_t nitems = 0) {
+    // Scenes with brute-force triangles: the few pixels that see the mesh cost ~100x more than the rest and
+    // sit next to each other.  A multiplicative permutation of the item order deals them out one or two per
+    // warp, so (a) the cooperative triangle scan applies (few lanes need it) and (b) no warp inherits a long
+    // serial chain of heavy pixels.  Which lane renders which pixel never affects results.
+    if (P.scatter_mul && nitems) w = (uint32_t)(((unsigned long long)w * P.scatter_mul) % nitems);
     const uint32_t tiles_x = (uint32_t)(P.W + 7) >> 3;
     const uint32_t tile = w >> 5, lit = w & 31;
     const uint32_t ty = tile / tiles_x, tx = tile - ty * tiles_x;
@@ -112,7 +119,7 @@ PT_DEV bool item_to_pixel(const LaunchArgs &P, uint32_t w, int &i, int &j) {
 }
 
 template <int VARIANT, bool FMA, int MEM, bool REGEN>
-__global__ void __launch_bounds__(128, VARIANT == PT_VARIANT_GRID ? 6 : 8) k_sm_pixel(const __grid_constant__ LaunchArgs P, uint32_t nitems, uint32_t *work_counter) {
+__global__ void __launch_bounds__(128, 6) k_sm_pixel(const __grid_constant__ LaunchArgs P, uint32_t nitems, uint32_t *work_counter) {
     constexpr bool CARRY = VARIANT != PT_VARIANT_BASE;
     constexpr bool GRID = VARIANT == PT_VARIANT_GRID;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -146,7 +153,7 @@ __global__ void __launch_bounds__(128, VARIANT == PT_VARIANT_GRID ? 6 : 8) k_sm_
                 int i, j;
                 if (w >= nitems) {
                     want = false;                      // queue exhausted
-                } else if (item_to_pixel(P, w, i, j)) {
+                } else if (item_to_pixel(P, w, i, j, nitems)) {
                     L.px = i; L.py = j;
                     L.rng = rng_seed(P.seeds, (uint32_t)(j * P.W + i));
                     L.phase = 0; s = 0; cx = cy = cz = 13.0f;
@@ -242,9 +249,17 @@ __global__ void __launch_bounds__(256, 4) k_sm_nodof(const __grid_constant__ Lau
 }
 
 template <int VARIANT, bool FMA, int MEM>
-static int launch_sm_pixel(pt_ctx ctx, const LaunchArgs &args) {
+static int launch_sm_pixel(pt_ctx ctx, const LaunchArgs &args_in) {
+    LaunchArgs args = args_in;
+    args.ap.tri_coop = MEM == PT_SCENE_SMEM;
     const uint32_t tiles_x = (uint32_t)(args.W + 7) / 8, tiles_y = (uint32_t)(args.nrows + 3) / 4;
     const uint32_t nitems = tiles_x * tiles_y * 32u;
+    args.scatter_mul = 0;
+    if (VARIANT != PT_VARIANT_GRID && ctx->h_scene[0]->ntri > 0 && nitems > 4096) {
+        static const uint32_t primes[] = {40503u, 48271u, 69621u, 16807u, 65537u, 104729u};
+        for (uint32_t pr : primes)
+            if (std::gcd(pr, nitems) == 1u) { args.scatter_mul = pr; break; }
+    }
     const size_t smem = MEM == PT_SCENE_SMEM ? (size_t)args.scene_bytes : 0;
     auto kern = k_sm_pixel<VARIANT, FMA, MEM, true>;
     int per_sm = 0;
