@@ -17,13 +17,21 @@ namespace pt {
 __constant__ SceneBlock c_scene;
 
 // Stage the used part of the scene block from global into shared memory (the _lmem idea, lmem:232-244,
-// without its "work-group must be at least ntriangles big" limitation).
+// without its "work-group must be at least ntriangles big" limitation): ONE bulk asynchronous copy (TMA,
+// cp.async.bulk -> UBLKCP) issued by thread 0 and an mbarrier the whole CTA waits on, instead of a
+// load/store loop through registers.
 PT_DEV const SceneBlock *stage_scene_smem(const LaunchArgs &P, unsigned char *smem) {
-    const uint4 *src = reinterpret_cast<const uint4 *>(P.gscene);
-    uint4 *dst = reinterpret_cast<uint4 *>(smem);
-    const int n16 = P.scene_bytes >> 4;
-    for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
+    __shared__ __align__(8) uint64_t s_stage_bar;
+    if (threadIdx.x == 0) {
+        mbar_init(&s_stage_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&s_stage_bar, (uint32_t)P.scene_bytes);
+        tma_load_1d(smem, P.gscene, (uint32_t)P.scene_bytes, &s_stage_bar);
+    }
+    mbar_wait(&s_stage_bar, 0);
     return reinterpret_cast<const SceneBlock *>(smem);
 }
 

@@ -443,6 +443,7 @@ static int fill_args(pt_ctx c, const pt_camera *cam, const pt_render_params *p, 
     for (int i = 0; i < 5; ++i) A->ap.lights[i] = hs->lights[i];
     A->ap.mesh_cx = c->mesh_c[0]; A->ap.mesh_cy = c->mesh_c[1]; A->ap.mesh_cz = c->mesh_c[2];
     A->ap.mesh_r2 = p->no_cull ? INFINITY : c->mesh_r2;
+    A->ap.ntri_hint = p->variant == PT_VARIANT_GRID ? 0 : hs->ntri;
     A->ap.tri_coop = 0;    // set by the launchers that stage the records in shared memory
     return 0;
 }
