@@ -310,7 +310,13 @@ def bench_ours(args, w, wname):
             raise SystemExit("--gpus %d needs torchrun --nproc-per-node %d" % (args.gpus, args.gpus))
     torch.cuda.set_device(local_rank)
     dist = None
+    saved_stdout = None
     if world > 1:
+        # NCCL prints its version banner on stdout; the contract is ONE JSON line there -> park stdout on stderr
+        os.environ["NCCL_DEBUG"] = os.environ.get("PT_NCCL_DEBUG", "WARN")
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -462,7 +468,12 @@ def bench_ours(args, w, wname):
                     line["reference_opencl_same_gpu"] = ocl
             except Exception as exc:  # pragma: no cover - reporting only
                 line["cpu_baseline"] = {"error": str(exc)}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        if saved_stdout is not None:
+            os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        if saved_stdout is not None:
+            os.dup2(2, 1)
     r.close()
     tmp.cleanup()
     if world > 1:
