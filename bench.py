@@ -453,6 +453,13 @@ def bench_ours(args, w, wname):
                          "hbm_achieved_gbs": out_bytes / (kernel_ms * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak,
                          "hbm_peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s"},
         }
+        try:
+            ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_reference_numbers.json"))).get(wname)
+            if ncu and world == 1:
+                line["roofline"]["traffic"] = ncu["dram_bytes_read"] + ncu["dram_bytes_write"]
+                line["roofline"]["ncu"] = ncu
+        except Exception:
+            pass
         if world == 1 and not args.no_cpu_baseline:
             try:
                 with tempfile.TemporaryDirectory() as t2:
