@@ -320,7 +320,7 @@ def bench_ours(args, w, wname):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    W, H, spp = w["W"], w["H"] * world, w["spp"]
+    W, H, spp = w["W"], (w["H"] if args.strong else w["H"] * world), w["spp"]
     tmp = tempfile.TemporaryDirectory()
     d = scene_dir_for(w, tmp.name)
     scene = load_workload_scene(w, d)
@@ -432,7 +432,7 @@ def bench_ours(args, w, wname):
         out_bytes = W * H * 4 / world
         line = {
             "metric": "Mrays/s", "value": rays / 1e3 / ms_per_step, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wname, "description": w["desc"], "width": W, "height": H, "spp": spp, "seeds": list(SEEDS),
                        "kernel": args.kernel, "scene_mem": args.scene_mem or "auto",
@@ -497,6 +497,7 @@ def main():
     ap.add_argument("--kernel", default="auto", choices=["auto", "mega", "persistent", "wavefront"])
     ap.add_argument("--scene-mem", default=None, choices=["auto", "const", "smem"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strong", action="store_true", help="N>1: keep the image fixed (strong scaling) instead of growing it with N")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":

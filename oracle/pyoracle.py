@@ -67,6 +67,8 @@ class OracleLib:
         L.oracle_randomize_id.argtypes = [C.c_uint32]
         L.oracle_build_grid.restype = C.c_uint64
         L.oracle_trace_ray.restype = C.c_int
+        L.oracle_save_pam.restype = C.c_int
+        L.oracle_save_pam.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p]
         assert L.oracle_contract_mode() == self.contract
 
     # ---- host-side restatements -------------------------------------------------------------
@@ -122,6 +124,10 @@ class OracleLib:
         refs = np.zeros(max(int(total), 1), np.uint32)
         self.lib.oracle_build_grid(*a, start.ctypes.data_as(C.c_void_p), refs.ctypes.data_as(C.c_void_p))
         return start, refs[: int(total)]
+
+    def save_pam(self, path, image):
+        img = np.ascontiguousarray(image, np.uint8)
+        return self.lib.oracle_save_pam(path.encode(), img.shape[1], img.shape[0], img.ctypes.data_as(C.c_void_p))
 
     # ---- device-side restatement ------------------------------------------------------------
     def rng_kat(self, seeds, gid, nsteps):

@@ -32,5 +32,5 @@ def test_result_ppm_identical(oracle_sep, scene_dirs, tmp_path, variant, size):
     ref_img = np.frombuffer(raw[k:], np.uint8).reshape(h, w, 4)
     out = oracle_sep.render(variant, w, h, SEED_SETS[1], oracle_sep.load_scene_dir(d, variant), want_rng=False, want_accum=False)
     assert np.array_equal(out["image"], ref_img)
-    oracle_sep.lib.oracle_save_pam(os.path.join(str(tmp_path), "o.ppm").encode(), w, h, out["image"].ctypes.data)
+    oracle_sep.save_pam(os.path.join(str(tmp_path), "o.ppm"), out["image"])
     assert open(os.path.join(str(tmp_path), "o.ppm"), "rb").read() == raw
