@@ -112,6 +112,13 @@ PTCUDA_SYMBOLS = {
     "pt_tonemap_device": (_I, [_VP, _VP, _VP, _I, _I]),
     "pt_render_host": (_I, [_VP, C.POINTER(pt_scene), C.POINTER(pt_grid), C.POINTER(pt_camera),
                             C.POINTER(pt_render_params), C.POINTER(C.c_uint8)]),
+    "pt_multi_create": (_VP, [_I]),
+    "pt_multi_destroy": (None, [_VP]),
+    "pt_multi_set_scene": (_I, [_VP, C.POINTER(pt_scene)]),
+    "pt_multi_build_grid": (_VP, [_VP, C.POINTER(pt_grid)]),
+    "pt_multi_launch_pathtracer": (_VP, [_VP, C.POINTER(pt_camera), C.POINTER(pt_render_params)]),
+    "pt_multi_map_render": (_VP, [_VP, C.POINTER(_VP)]),
+    "pt_multi_get_counters": (_I, [_VP, C.POINTER(pt_counters)]),
     "pt_wait": (_I, [_VP]),
     "pt_runtime_ms": (_D, [_VP]),
     "pt_release_event": (None, [_VP]),

@@ -16,6 +16,8 @@
  *                      the mesh's bounding sphere skip it; identical results)
  *   PT_MAX_TRIANGLES=n lift the 512 / 65536 MAX_TRIANGLES cap of the reference hosts
  *   PT_DEVICE / OCL_DEVICE   device index
+ *   PT_GPUS=n          render on GPUs 0..n-1 of this box (row stripes + one NCCL reduce of the accumulation buffer)
+ *   PT_NO_WARMUP=1     skip the untimed one-row warm-up launch
  *   PT_STATS=1         append Mrays/s, samples/s and work counters after the reference's own lines
  */
 #define _GNU_SOURCE
@@ -55,7 +57,9 @@ int pth_cli_main(int variant, int argc, char **argv) {
     printf("number of platforms: %u\n", 1u);
     printf("selected platform %d: %s\n", 0, "NVIDIA CUDA (libptcuda, sm_100a)");
     int dev = pt_select_device();
-    pt_ctx ctx = pt_create(dev);
+    const int ngpus = getenv("PT_GPUS") ? atoi(getenv("PT_GPUS")) : 1;
+    pt_multi multi = ngpus > 1 ? pt_multi_create(ngpus) : NULL;
+    pt_ctx ctx = multi ? NULL : pt_create(dev);
     time_t now = time(NULL);
     printf("compiling:\n// %s#include \"%s\"\n", ctime(&now), "pathtracer.ocl");
     printf("=== BUILD LOG ===\n%s\n=========\n", "kernels are precompiled CUDA for sm_100a (libptcuda.so); nothing to build\n");
@@ -105,9 +109,9 @@ int pth_cli_main(int variant, int argc, char **argv) {
     printf("Number of triangles: %d\n", scene.ntriangles);
     printf("Number of lights: %d\n", scene.nlights);
 
-    pt_set_scene(ctx, &scene);
+    if (multi) pt_multi_set_scene(multi, &scene); else pt_set_scene(ctx, &scene);
     pt_event grid_evt = NULL;
-    if (grid) grid_evt = pt_build_grid(ctx, &gdesc);
+    if (grid) grid_evt = multi ? pt_multi_build_grid(multi, &gdesc) : pt_build_grid(ctx, &gdesc);
 
     static const char *const kernels[] = {"mega", "persistent", "wavefront", "auto", "grid_tma"};
     static const char *const mems[] = {"const", "smem", "auto"};
@@ -124,9 +128,19 @@ int pth_cli_main(int variant, int argc, char **argv) {
     rp.arith = env_choice("PT_ARITH", ariths, 2, PT_ARITH_FMA);
     rp.no_cull = getenv("PT_NO_CULL") ? atoi(getenv("PT_NO_CULL")) : 0;
 
-    pt_event render_evt = pt_launch_pathtracer(ctx, &cam, &rp);
+    if (!getenv("PT_NO_WARMUP")) {
+        /* One untimed single-row launch first: CUDA loads kernel code lazily (and NCCL sets up its rings) on first
+         * use, which the reference's OpenCL event times never include (its JIT runs in clBuildProgram). */
+        pt_render_params warm = rp;
+        warm.row_begin = 0;
+        warm.row_end = 1;
+        pt_event w = multi ? pt_multi_launch_pathtracer(multi, &cam, &warm) : pt_launch_pathtracer(ctx, &cam, &warm);
+        pt_wait(w);
+        pt_release_event(w);
+    }
+    pt_event render_evt = multi ? pt_multi_launch_pathtracer(multi, &cam, &rp) : pt_launch_pathtracer(ctx, &cam, &rp);
     pt_event read_evt = NULL;
-    void *pixels = pt_map_render(ctx, &read_evt);
+    void *pixels = multi ? pt_multi_map_render(multi, &read_evt) : pt_map_render(ctx, &read_evt);
 
     const char *image_name = "result.ppm";
     if (pth_save_pam(image_name, img_width, img_height, pixels) != 0) {
@@ -155,11 +169,11 @@ int pth_cli_main(int variant, int argc, char **argv) {
 
     if (getenv("PT_STATS")) {
         pt_counters c;
-        pt_get_counters(ctx, &c);
+        if (multi) pt_multi_get_counters(multi, &c); else pt_get_counters(ctx, &c);
         printf("PT_STATS {\"variant\": %d, \"width\": %d, \"height\": %d, \"spp\": %d, \"kernel\": \"%s\", \"scene_mem\": \"%s\", "
-               "\"arith\": \"%s\", \"render_ms\": %.6f, \"samples\": %llu, \"rays\": %llu, \"shadow_rays\": %llu, "
+               "\"arith\": \"%s\", \"gpus\": %d, \"render_ms\": %.6f, \"samples\": %llu, \"rays\": %llu, \"shadow_rays\": %llu, "
                "\"tri_tests\": %llu, \"cells_visited\": %llu, \"prim_tests\": %llu, \"mrays_per_s\": %.3f, \"msamples_per_s\": %.3f}\n",
-               variant, img_width, img_height, rp.spp, kernels[rp.kernel], mems[rp.scene_mem], ariths[rp.arith], render_ms,
+               variant, img_width, img_height, rp.spp, kernels[rp.kernel], mems[rp.scene_mem], ariths[rp.arith], ngpus, render_ms,
                (unsigned long long)c.samples, (unsigned long long)c.rays, (unsigned long long)c.shadow_rays,
                (unsigned long long)c.tri_tests, (unsigned long long)c.cells_visited, (unsigned long long)c.prim_tests,
                c.rays / 1.0e3 / render_ms, c.samples / 1.0e3 / render_ms);
@@ -169,6 +183,6 @@ int pth_cli_main(int variant, int argc, char **argv) {
     pt_release_event(read_evt);
     pt_release_event(grid_evt);
     free(tris);
-    pt_destroy(ctx);
+    if (multi) pt_multi_destroy(multi); else pt_destroy(ctx);
     return 0;
 }

@@ -8,6 +8,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <dlfcn.h>
+
 #include <atomic>
 #include <new>
 
@@ -665,5 +667,159 @@ extern "C" int pt_render_host(pt_ctx c, const pt_scene *scene, const pt_grid *gr
     pt_release_event(e);
     if (!h) return 1;
     memcpy(rgba8_out, h, (size_t)p->width * p->height * 4);
+    return 0;
+}
+
+
+// ------------------------------------------------------------------------- single-process multi-GPU
+// NCCL is reached through dlopen so that libptcuda.so carries no link-time dependency on it (a process
+// that already loaded torch's bundled libnccl.so.2 keeps using that one).  Minimal local declarations of the
+// few entry points used (public NCCL API: ncclCommInitAll, ncclReduce, group calls).
+typedef struct ncclComm *pt_ncclComm_t;
+enum { PT_NCCL_FLOAT32 = 7, PT_NCCL_SUM = 0 };
+struct pt_nccl_api {
+    void *lib;
+    int (*CommInitAll)(pt_ncclComm_t *, int, const int *);
+    int (*CommDestroy)(pt_ncclComm_t);
+    int (*GroupStart)(void);
+    int (*GroupEnd)(void);
+    int (*Reduce)(const void *, void *, size_t, int, int, int, pt_ncclComm_t, cudaStream_t);
+    const char *(*GetErrorString)(int);
+};
+
+struct pt_multi_s {
+    int n;
+    pt_ctx ctx[16];
+    float4 *accum[16];
+    uint32_t *rgba_scratch[16];
+    size_t cap_pixels;
+    pt_nccl_api nccl;
+    pt_ncclComm_t comms[16];
+    int last_w, last_h;
+};
+
+static int nccl_load(pt_nccl_api *a) {
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    a->lib = nullptr;
+    for (const char *nm : names) {
+        a->lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (a->lib) break;
+    }
+    if (!a->lib) return pt_fail(1, "pt_multi_create: cannot load libnccl.so.2 (%s)", dlerror());
+    *(void **)&a->CommInitAll = dlsym(a->lib, "ncclCommInitAll");
+    *(void **)&a->CommDestroy = dlsym(a->lib, "ncclCommDestroy");
+    *(void **)&a->GroupStart = dlsym(a->lib, "ncclGroupStart");
+    *(void **)&a->GroupEnd = dlsym(a->lib, "ncclGroupEnd");
+    *(void **)&a->Reduce = dlsym(a->lib, "ncclReduce");
+    *(void **)&a->GetErrorString = dlsym(a->lib, "ncclGetErrorString");
+    if (!a->CommInitAll || !a->CommDestroy || !a->GroupStart || !a->GroupEnd || !a->Reduce)
+        return pt_fail(1, "pt_multi_create: libnccl lacks a required symbol");
+    return 0;
+}
+
+extern "C" pt_multi pt_multi_create(int ngpus) {
+    if (ngpus < 1 || ngpus > 16 || ngpus > pt_device_count()) { pt_fail(1, "pt_multi_create: %d GPUs requested, %d visible", ngpus, pt_device_count()); return nullptr; }
+    pt_multi m = (pt_multi)calloc(1, sizeof(pt_multi_s));
+    m->n = ngpus;
+    for (int i = 0; i < ngpus; ++i) {
+        m->ctx[i] = pt_create(i);
+        if (!m->ctx[i]) return nullptr;
+    }
+    if (ngpus > 1) {
+        if (nccl_load(&m->nccl)) return nullptr;
+        int devs[16];
+        for (int i = 0; i < ngpus; ++i) devs[i] = i;
+        int rc = m->nccl.CommInitAll(m->comms, ngpus, devs);
+        if (rc) { pt_fail(rc, "ncclCommInitAll: %s", m->nccl.GetErrorString ? m->nccl.GetErrorString(rc) : "?"); return nullptr; }
+    }
+    return m;
+}
+
+extern "C" void pt_multi_destroy(pt_multi m) {
+    if (!m) return;
+    for (int i = 0; i < m->n; ++i) {
+        cudaSetDevice(i);
+        if (m->n > 1 && m->comms[i]) m->nccl.CommDestroy(m->comms[i]);
+        cudaFree(m->accum[i]);
+        cudaFree(m->rgba_scratch[i]);
+        pt_destroy(m->ctx[i]);
+    }
+    free(m);
+}
+
+extern "C" int pt_multi_set_scene(pt_multi m, const pt_scene *scene) {
+    for (int i = 0; i < m->n; ++i) {
+        int rc = pt_set_scene(m->ctx[i], scene);     // the scene is replicated on every device
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+extern "C" pt_event pt_multi_build_grid(pt_multi m, const pt_grid *grid) {
+    pt_event first = nullptr;
+    for (int i = 0; i < m->n; ++i) {
+        pt_event e = pt_build_grid(m->ctx[i], grid);
+        if (!e) return nullptr;
+        if (i == 0) first = e; else pt_release_event(e);
+    }
+    return first;
+}
+
+extern "C" pt_event pt_multi_launch_pathtracer(pt_multi m, const pt_camera *cam, const pt_render_params *params) {
+    if (m->n == 1) return pt_launch_pathtracer(m->ctx[0], cam, params);
+    const size_t npix = (size_t)params->width * params->height;
+    for (int i = 0; i < m->n; ++i) {
+        PT_CUDA_NULL(cudaSetDevice(i), "select device");
+        if (m->cap_pixels < npix) {
+            cudaFree(m->accum[i]); cudaFree(m->rgba_scratch[i]);
+            PT_CUDA_NULL(cudaMalloc(&m->accum[i], npix * 16), "alloc accumulation buffer");
+            PT_CUDA_NULL(cudaMalloc(&m->rgba_scratch[i], npix * 4), "alloc scratch image");
+        }
+    }
+    m->cap_pixels = m->cap_pixels < npix ? npix : m->cap_pixels;
+    pt_ctx c0 = m->ctx[0];
+    PT_CUDA_NULL(cudaSetDevice(0), "select device");
+    if (ensure_dev((void **)&c0->d_rgba, &c0->rgba_cap, npix * 4)) return nullptr;
+    pt_event e = event_new(c0);
+    if (!e) return nullptr;
+    cudaEventRecord(e->start, c0->stream);
+    for (int i = 0; i < m->n; ++i) {
+        PT_CUDA_NULL(cudaSetDevice(i), "select device");
+        pt_render_params p = *params;
+        p.row_interleave = 8; p.rank = i; p.nranks = m->n;
+        PT_CUDA_NULL(cudaMemsetAsync(m->accum[i], 0, npix * 16, m->ctx[i]->stream), "clear accumulation buffer");
+        if (pt_render_device(m->ctx[i], cam, &p, m->rgba_scratch[i], m->accum[i])) return nullptr;
+    }
+    // the only collective: sum the accumulation buffers onto device 0 (rows a device does not own are zero)
+    m->nccl.GroupStart();
+    for (int i = 0; i < m->n; ++i) {
+        int rc = m->nccl.Reduce(m->accum[i], m->accum[i], npix * 4, PT_NCCL_FLOAT32, PT_NCCL_SUM, 0, m->comms[i], m->ctx[i]->stream);
+        if (rc) { pt_fail(rc, "ncclReduce failed"); return nullptr; }
+    }
+    m->nccl.GroupEnd();
+    PT_CUDA_NULL(cudaSetDevice(0), "select device");
+    if (pt_tonemap_device(c0, m->accum[0], c0->d_rgba, params->width, params->height)) return nullptr;
+    cudaEventRecord(e->stop, c0->stream);
+    c0->last_w = params->width; c0->last_h = params->height; c0->last_variant = params->variant;
+    m->last_w = params->width; m->last_h = params->height;
+    return e;
+}
+
+extern "C" void *pt_multi_map_render(pt_multi m, pt_event *evt) {
+    for (int i = 1; i < m->n; ++i) { cudaSetDevice(i); cudaStreamSynchronize(m->ctx[i]->stream); }
+    cudaSetDevice(0);
+    return pt_map_render(m->ctx[0], evt);
+}
+
+extern "C" int pt_multi_get_counters(pt_multi m, pt_counters *out) {
+    memset(out, 0, sizeof(*out));
+    for (int i = 0; i < m->n; ++i) {
+        pt_counters c;
+        cudaSetDevice(i);
+        int rc = pt_get_counters(m->ctx[i], &c);
+        if (rc) return rc;
+        out->samples += c.samples; out->rays += c.rays; out->shadow_rays += c.shadow_rays; out->tri_tests += c.tri_tests;
+        out->cells_visited += c.cells_visited; out->prim_tests += c.prim_tests; out->tri_tests_executed += c.tri_tests_executed;
+    }
     return 0;
 }

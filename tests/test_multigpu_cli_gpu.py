@@ -1,0 +1,33 @@
+"""Single-process multi-GPU path of the drop-in executables (PT_GPUS=n): row stripes + one NCCL reduce of the
+accumulation buffer must give a result.ppm byte-identical to the single-GPU run.  Needs >= 2 GPUs (skipped on
+the 1-GPU test box; exercised with `gpurun --gpus 2`)."""
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+from opencl_montecarlo_path_tracing_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+BIN = os.path.join(ROOT, "opencl_montecarlo_path_tracing_b200", "bin")
+
+
+@pytest.mark.parametrize("variant,dirname", [("nodof", "CLSuperPathTracer_lmem_NoDoF"), ("grid", "CLSuperPathTracer_trianglegrid"),
+                                             ("base", "CLSuperPathTracer")])
+def test_pt_gpus_is_bit_identical(scene_dirs, variant, dirname):
+    ngpu = _lib.cuda_lib().pt_device_count()
+    if ngpu < 2:
+        pytest.skip("needs at least 2 GPUs")
+    exe = os.path.join(BIN, dirname, "CLSuperPathTracer")
+    d = scene_dirs[variant]
+    imgs = {}
+    for n in (1, min(ngpu, 8)):
+        env = dict(os.environ, PT_SEEDS="1,2,3,4", PT_GPUS=str(n), PT_STATS="1")
+        p = subprocess.run([exe, "640", "360"], cwd=d, env=env, capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, p.stdout + p.stderr
+        imgs[n] = open(os.path.join(d, "result.ppm"), "rb").read()
+        print(variant, n, re.search(r"rendering : .*", p.stdout).group(0))
+    a, b = imgs.values()
+    assert a == b
