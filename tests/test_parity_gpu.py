@@ -226,3 +226,28 @@ def test_many_analytic_primitives(renderer, scene_dirs, oracle_fma, kernel):
         assert np.array_equal(res.accum[r0:r1].view(np.uint32), ref["accum"][r0:r1].view(np.uint32))
         assert np.array_equal(res.rng_state.reshape(H, W, 4)[r0:r1], ref["rng_state"].reshape(H, W, 4)[r0:r1])
         assert res.counters["prim_tests"] == ref["counters"]["prim_tests"]
+
+
+def test_full_size_flavours_agree(renderer, scene_dirs):
+    """At BASELINE.json's full image size (1920x1080) the oracle is too slow to render whole frames, so the
+    size-independent property is checked instead: every kernel flavour, both scene memories and a 3-way row
+    tiling produce bit-identical accumulation buffers (spp reduced to 16; work is identical per sample)."""
+    W, H, spp = 1920, 1080, 16
+    for variant, flavours in (("base", ("mega", "persistent", "wavefront")), ("nodof", ("mega", "persistent", "wavefront")),
+                              ("grid", ("mega", "persistent", "wavefront", "grid_tma"))):
+        scene = pt.load_scene_dir(scene_dirs[variant], variant)
+        renderer.set_scene(scene)
+        if variant == "grid":
+            renderer.build_grid(pt.grid_dims(scene))
+        s = 64 if variant == "nodof" else spp
+        ref = renderer.render(variant, W, H, SEED_SETS[0], spp=s, kernel=flavours[0], want_accum=True)
+        assert (ref.image[..., 3] == 255).all()
+        for k in flavours[1:]:
+            got = renderer.render(variant, W, H, SEED_SETS[0], spp=s, kernel=k, want_accum=True)
+            assert np.array_equal(got.accum.view(np.uint32), ref.accum.view(np.uint32)), (variant, k)
+            assert got.counters["rays"] == ref.counters["rays"]
+        other_mem = renderer.render(variant, W, H, SEED_SETS[0], spp=s, kernel=flavours[0], scene_mem="const", want_accum=True)
+        assert np.array_equal(other_mem.accum.view(np.uint32), ref.accum.view(np.uint32))
+        parts = [renderer.render(variant, W, H, SEED_SETS[0], spp=s, rows=r, want_accum=True).accum for r in ((0, 300), (300, 777), (777, 1080))]
+        tiled = np.concatenate([parts[0][:300], parts[1][300:777], parts[2][777:]])
+        assert np.array_equal(tiled.view(np.uint32), ref.accum.view(np.uint32)), variant
