@@ -54,7 +54,7 @@ struct pt_ctx_s {
     pt::SceneBlock *h_scene[2];   // [PT_ARITH_SEPARATE], [PT_ARITH_FMA] (normals differ)
     pt::SceneBlock *d_scene[2];
     int scene_bytes;
-    float mesh_c[3], mesh_r2;     // bounding sphere of the brute-force mesh (conservative cull)
+    float mesh_c[3], mesh_r, mesh_k;  // bounding sphere of the brute-force mesh + distance-proportional margin (conservative cull)
     float *d_tris_raw;            // ntri_total x 12 floats (grid build input)
     int ntri_total;
 

@@ -266,9 +266,17 @@ extern "C" int pt_set_scene(pt_ctx c, const pt_scene *sc) {
                 if (q > r2) r2 = q;
             }
         double r = sqrt(r2) * 1.01 + 0.01;
+        double kmax = 0;     // max |e0||e2| over the brute-force triangles
+        for (int i = 0; i < nbrute; ++i) {
+            const float *t = sc->triangles + 12 * (size_t)i;
+            double e0 = sqrt(pow((double)t[4] - t[0], 2) + pow((double)t[5] - t[1], 2) + pow((double)t[6] - t[2], 2));
+            double e2 = sqrt(pow((double)t[8] - t[0], 2) + pow((double)t[9] - t[1], 2) + pow((double)t[10] - t[2], 2));
+            if (e0 * e2 > kmax) kmax = e0 * e2;
+        }
         for (int a = 0; a < 3; ++a) c->mesh_c[a] = (float)ctr[a];
-        c->mesh_r2 = (float)(r * r * 1.001 + 0.01);
-        if (!(c->mesh_r2 == c->mesh_r2) || !isfinite(c->mesh_r2)) c->mesh_r2 = INFINITY;
+        c->mesh_r = (float)r;
+        c->mesh_k = (float)(2e-4 * kmax + 1e-6);
+        if (!isfinite(c->mesh_r) || !isfinite(c->mesh_k)) c->mesh_r = INFINITY;
     }
     for (int a = 0; a < 2; ++a)
         PT_CUDA(cudaMemcpyAsync(c->d_scene[a], c->h_scene[a], sizeof(SceneBlock), cudaMemcpyHostToDevice, c->stream),
@@ -444,7 +452,28 @@ static int fill_args(pt_ctx c, const pt_camera *cam, const pt_render_params *p, 
     for (int i = 0; i < PT_FAST_PRIMS; ++i) { A->ap.sq[i] = hs->sq[i]; A->ap.sp[i] = hs->sp[i]; }
     for (int i = 0; i < 5; ++i) A->ap.lights[i] = hs->lights[i];
     A->ap.mesh_cx = c->mesh_c[0]; A->ap.mesh_cy = c->mesh_c[1]; A->ap.mesh_cz = c->mesh_c[2];
-    A->ap.mesh_r2 = p->no_cull ? INFINITY : c->mesh_r2;
+    A->ap.mesh_r = p->no_cull ? INFINITY : c->mesh_r;
+    A->ap.mesh_k = c->mesh_k;
+    {
+        // bounding box of all squares (x in [k-1,k+1], |y| <= 1, z = 4+j) and unit spheres (centre (k,0,j+4))
+        float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+        for (int i = 0; i < hs->nsq; ++i) {
+            const float k = hs->sq[i].x, z = hs->sq[i].y;
+            lo[0] = fminf(lo[0], k - 1.f); hi[0] = fmaxf(hi[0], k + 1.f);
+            lo[1] = fminf(lo[1], -1.f);    hi[1] = fmaxf(hi[1], 1.f);
+            lo[2] = fminf(lo[2], z);       hi[2] = fmaxf(hi[2], z);
+        }
+        for (int i = 0; i < hs->nsp; ++i) {
+            const float k = -hs->sp[i].x, z = -hs->sp[i].y;
+            lo[0] = fminf(lo[0], k - 1.f); hi[0] = fmaxf(hi[0], k + 1.f);
+            lo[1] = fminf(lo[1], -1.f);    hi[1] = fmaxf(hi[1], 1.f);
+            lo[2] = fminf(lo[2], z - 1.f); hi[2] = fmaxf(hi[2], z + 1.f);
+        }
+        for (int a = 0; a < 3; ++a) {
+            A->ap.box_lo[a] = p->no_cull ? -INFINITY : lo[a];      // the per-ray margin is added on the device
+            A->ap.box_hi[a] = p->no_cull ? INFINITY : hi[a];
+        }
+    }
     A->ap.ntri_hint = p->variant == PT_VARIANT_GRID ? 0 : hs->ntri;
     A->ap.tri_coop = 0;    // set by the launchers that stage the records in shared memory
     return 0;
