@@ -482,7 +482,17 @@ static int fill_args(pt_ctx c, const pt_camera *cam, const pt_render_params *p, 
 // PT_KERNEL_AUTO / PT_SCENE_AUTO: measured best per variant on B200
 static pt_render_params resolve_auto(const pt_render_params *in) {
     pt_render_params p = *in;
-    if (p.kernel == PT_KERNEL_AUTO) p.kernel = p.variant == PT_VARIANT_NODOF ? PT_KERNEL_PERSISTENT : PT_KERNEL_MEGA;
+    if (p.kernel == PT_KERNEL_AUTO) {
+        if (p.variant == PT_VARIANT_NODOF) p.kernel = PT_KERNEL_PERSISTENT;
+        else if (p.variant == PT_VARIANT_GRID) p.kernel = PT_KERNEL_MEGA;
+        else {
+            // brute-force triangle scenes: a pixel that sees the mesh is a ~1.7 ms serial chain at 64 spp.  Small
+            // frames are bounded by that tail -> scatter heavy pixels over warps (persistent + cooperative scan);
+            // large frames have enough heavy tiles to fill the GPU, where the dense lane-serial scan is cheaper.
+            const long long pixels = (long long)p.width * (p.row_end > p.row_begin ? p.row_end - p.row_begin : p.height);
+            p.kernel = pixels <= 400000 ? PT_KERNEL_PERSISTENT : PT_KERNEL_MEGA;
+        }
+    }
     if (p.scene_mem == PT_SCENE_AUTO)
         p.scene_mem = (p.variant == PT_VARIANT_NODOF || p.variant == PT_VARIANT_GRID) ? PT_SCENE_CONST : PT_SCENE_SMEM;
     return p;
