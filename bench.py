@@ -410,7 +410,7 @@ def bench_ours(args, w, wname):
         t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t[0])
-    h2d = 2 * 27408 + scene.ntriangles * 48      # two arithmetic-policy scene blocks + raw triangles
+    h2d = 2 * (2848 + 48 * min(scene.ntriangles, 512)) + scene.ntriangles * 48   # two policy scene-block prefixes + raw triangles
     d2h = W * H * 4
     r2.close()
 

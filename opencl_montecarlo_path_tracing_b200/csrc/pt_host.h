@@ -56,6 +56,7 @@ struct pt_ctx_s {
     int scene_bytes;
     float mesh_c[3], mesh_r, mesh_k;  // bounding sphere of the brute-force mesh + distance-proportional margin (conservative cull)
     float *d_tris_raw;            // ntri_total x 12 floats (grid build input)
+    size_t tris_cap;              // capacity of d_tris_raw in triangles
     int ntri_total;
 
     // grid

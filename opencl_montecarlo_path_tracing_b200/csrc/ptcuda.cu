@@ -278,17 +278,20 @@ extern "C" int pt_set_scene(pt_ctx c, const pt_scene *sc) {
         c->mesh_k = (float)(2e-4 * kmax + 1e-6);
         if (!isfinite(c->mesh_r) || !isfinite(c->mesh_k)) c->mesh_r = INFINITY;
     }
-    for (int a = 0; a < 2; ++a)
-        PT_CUDA(cudaMemcpyAsync(c->d_scene[a], c->h_scene[a], sizeof(SceneBlock), cudaMemcpyHostToDevice, c->stream),
+    for (int a = 0; a < 2; ++a)      // only the used prefix of the block travels (header + primitives + kept triangles)
+        PT_CUDA(cudaMemcpyAsync(c->d_scene[a], c->h_scene[a], (size_t)c->scene_bytes, cudaMemcpyHostToDevice, c->stream),
                 "upload scene");
-    cudaFree(c->d_tris_raw);
-    c->d_tris_raw = nullptr;
     c->ntri_total = sc->ntriangles;
-    if (sc->ntriangles > 0) {
+    if ((size_t)sc->ntriangles > c->tris_cap) {       // the raw triangle buffer is reused across scene updates
+        cudaFree(c->d_tris_raw);
+        c->d_tris_raw = nullptr;
+        c->tris_cap = 0;
         PT_CUDA(cudaMalloc(&c->d_tris_raw, (size_t)sc->ntriangles * 48), "alloc triangles");
+        c->tris_cap = (size_t)sc->ntriangles;
+    }
+    if (sc->ntriangles > 0)
         PT_CUDA(cudaMemcpyAsync(c->d_tris_raw, sc->triangles, (size_t)sc->ntriangles * 48, cudaMemcpyHostToDevice, c->stream),
                 "upload triangles");
-    }
     PT_CUDA(cudaStreamSynchronize(c->stream), "sync scene upload");
     c->scene_set = true;
     c->grid_set = false;
