@@ -62,7 +62,7 @@ PT_DEV void flush_counters(const LaunchArgs &P, const Counters &c, int ntri_coun
 }
 
 template <int VARIANT, bool FMA, int MEM>
-__global__ void __launch_bounds__(128, 6) k_mega_pixel(const __grid_constant__ LaunchArgs P) {
+__global__ void __launch_bounds__(128, VARIANT == PT_VARIANT_GRID ? 8 : 6) k_mega_pixel(const __grid_constant__ LaunchArgs P) {
     constexpr bool CARRY = VARIANT != PT_VARIANT_BASE;
     constexpr bool GRID = VARIANT == PT_VARIANT_GRID;
     extern __shared__ __align__(16) unsigned char smem_raw[];
