@@ -7,6 +7,7 @@
  * "lmem"  = CLSuperPathTracer_lmem/pathtracer.ocl
  * "nodof" = CLSuperPathTracer_lmem_NoDoF/pathtracer.ocl
  * "grid"  = CLSuperPathTracer_trianglegrid/pathtracer.ocl
+ * "bidir" = CLSuperBidirectionalPathTracer/bidirectionalpathtracer.ocl
  */
 #include "oracle.h"
 
@@ -107,6 +108,16 @@ static inline void rng_next(Rng *s, float *u0, float *u1, uint32_t *raw0, uint32
     if (raw1) *raw1 = r1;
 }
 
+/* bidir:12-23 with the limits (-1, 1) of bidir:320: (1 - -1)/4294967295 -> 2^-31; the product is exact, the
+ * addition of -1 rounds once (so a contracted fma gives the same value). */
+static inline void rng_next_pm1(Rng *s, float *u0, float *u1) {
+    float a, b; uint32_t r0, r1;
+    rng_next(s, &a, &b, &r0, &r1);
+    const float scale = (1.0f - -1.0f) / 4294967296.0f;
+    *u0 = -1.0f + (float)r0 * scale;
+    *u1 = -1.0f + (float)r1 * scale;
+}
+
 void oracle_rng_kat(const uint32_t seeds[4], uint32_t gid, int nsteps, float *out_f, uint32_t *out_u32,
                     uint32_t out_state[4]) {
     Rng s = rng_seed(seeds, gid);
@@ -129,6 +140,7 @@ typedef struct {
     const float (*lights)[4]; int nlights;
     V3 box_min, box_max; int res[3]; V3 cell;
     const uint32_t *cell_start, *cell_refs;
+    int bidir; const float *vpls; int nvpl;
 } Scene;
 
 /* base:111-134 / grid:61-85 — Moller-Trumbore on one triangle; returns 1 if *t improved */
@@ -255,6 +267,37 @@ static inline V3 sample(const Scene *S, V3 o, V3 d, Rng *rng, oracle_counters *c
     }
     V3 X = vmadd(d, t, o);
     float illum = 0.0f;
+    if (S->bidir) {
+        /* bidir:165-187 — every VPL, unshadowed */
+        for (int i = 0; i < S->nvpl; ++i) {
+            const float *P = S->vpls + 4 * (size_t)i;
+            float I = P[3];
+            if (I == 0.0f) continue;
+            V3 dv = vsub(v3(P[0], P[1], P[2]), X);
+            float dist = sqrtf(dot3(dv, dv));           /* distance(light_pos, intersection) */
+            V3 ld = v3(dv.x / dist, dv.y / dist, dv.z / dist);
+            float lam = dot3(ld, n);
+            if (lam < 0.0f) continue;
+            float f = I / (dist * dist);
+            f = 1.0f < f ? 1.0f : f;
+            illum = MADD(lam, f, illum);
+        }
+        if (illum > 1.0f) illum = 1.0f;
+        /* bidir:190-201 — soft shadows: each occluded real light SUBTRACTS 1/nlights; the shadow ray is bounded by
+         * the un-jittered distance to the light (t = distanceFromLight, TraceRay keeps the running bound) */
+        for (int i = 0; i < S->nlights; ++i) {
+            float r0, r1;
+            rng_next(rng, &r0, &r1, NULL, NULL);
+            V3 L = v3(S->lights[i][0], S->lights[i][1], S->lights[i][2]);
+            V3 dv = vsub(L, X);
+            float dist = sqrtf(dot3(dv, dv));
+            V3 ld = v3((L.x + r0) + X.x * -1.0f, (L.y + r1) + X.y * -1.0f, (L.z + 0.0f) + X.z * -1.0f);
+            ld = normalize3(ld);
+            t = dist;
+            cnt->shadow_rays++;
+            if (trace_ray(S, X, ld, &t, &dummy, cnt)) illum -= 1.0f / (float)S->nlights;
+        }
+    } else
     for (int i = 0; i < S->nlights; ++i) {
         float r0, r1;
         rng_next(rng, &r0, &r1, NULL, NULL);          /* drawn before any skip (base:168) */
@@ -274,7 +317,7 @@ static inline V3 sample(const Scene *S, V3 o, V3 d, Rng *rng, oracle_counters *c
         f = 1.0f < f ? 1.0f : f;                      /* min(x, 1.0f) = 1.0f < x ? 1.0f : x */
         illum = MADD(lam, f, illum);
     }
-    if (illum > 1.0f) illum = 1.0f;
+    if (!S->bidir && illum > 1.0f) illum = 1.0f;  /* bidir clamps BEFORE the shadow subtraction (bidir:188) */
     illum /= 4.0f;
     if (m == 1) {
         V3 Y = vscale(X, 0.2f);
@@ -318,6 +361,66 @@ static void scene_from_job(const oracle_job *J, Scene *S) {
     S->res[0] = J->grid_res[0]; S->res[1] = J->grid_res[1]; S->res[2] = J->grid_res[2];
     S->cell = v3(J->cell_size[0], J->cell_size[1], J->cell_size[2]);
     S->cell_start = J->cell_start; S->cell_refs = J->cell_refs;
+    S->bidir = J->variant == ORACLE_BIDIR;
+    S->vpls = J->vpls; S->nvpl = J->nvpl;
+}
+
+/* bidir:230-278 SampleFromLightSource — one ray from a light; the hit point becomes a VPL whose intensity is the
+ * light's Lambert term at the hit.  NB the reference dots the INCOMING direction with the outward normal, so
+ * only surfaces hit from behind (squares seen from below) ever get a non-zero VPL; triangles (material 4)
+ * and misses give the all-zero "dummy" light. */
+static inline void sample_from_light(const Scene *S, V3 o, V3 d, float I, int total_vlp, float out[4], oracle_counters *cnt) {
+    float t = 1e9f;
+    V3 n = v3(0, 0, 0);
+    out[0] = out[1] = out[2] = out[3] = 0.0f;
+    int m = trace_ray(S, o, d, &t, &n, cnt);
+    if (!m) return;
+    V3 X = vmadd(d, t, o);
+    float lam = dot3(d, n);
+    if (lam < 0.0f) lam = 0.0f;
+    else {
+        V3 dv = vsub(o, X);
+        float dist = sqrtf(dot3(dv, dv));
+        float f = I / (dist * dist);
+        f = 1.0f < f ? 1.0f : f;
+        lam = lam * f;
+    }
+    if (lam > 1.0f) lam = 1.0f;
+    float k = m == 1 ? 70.0f : (m == 2 ? 5.0f : (m == 3 ? 40.0f : 0.0f));
+    if (k == 0.0f) return;                              /* material 4: (float4)(0) */
+    out[0] = X.x; out[1] = X.y; out[2] = X.z;
+    out[3] = (k * lam) / (float)(total_vlp / 512);      /* integer division first (bidir:267) */
+}
+
+int oracle_light_tracer(const oracle_job *J, int n, float *vpl_out, uint32_t *rng_state, oracle_counters *counters) {
+    if (!J || n <= 0 || !vpl_out || J->nlights < 0 || J->nlights > 5) return -1;
+    oracle_job Jl = *J;
+    Jl.variant = ORACLE_LMEM;                            /* lmem TraceRay semantics, brute-force triangles */
+    Scene S;
+    scene_from_job(&Jl, &S);
+    oracle_counters cnt;
+    memset(&cnt, 0, sizeof(cnt));
+    const int total = n * J->nlights;
+    for (int gi = 0; gi < n; ++gi) {
+        Rng rng = rng_seed(J->seeds, (uint32_t)gi);
+        float r0 = 0.0f, r1 = 0.0f, sum = 2.0f;          /* randSum is NOT reset between lights (bidir:292,319): */
+        for (int l = 0; l < J->nlights; ++l) {           /* lights after the first reuse the same direction     */
+            while (sum >= 1.0f) {
+                rng_next_pm1(&rng, &r0, &r1);
+                sum = MADD(r1, r1, r0 * r0);
+            }
+            float sq = sqrtf(1.0f - sum);
+            V3 d = v3((2.0f * r0) * sq, (2.0f * r1) * sq, 1.0f - 2.0f * sum);
+            V3 o = v3(J->lights[l][0], J->lights[l][1], J->lights[l][2]);
+            sample_from_light(&S, o, d, J->lights[l][3], total, vpl_out + 4 * ((size_t)gi + (size_t)l * n), &cnt);
+        }
+        if (rng_state) {
+            uint32_t *q = rng_state + 4 * (size_t)gi;
+            q[0] = rng.x0; q[1] = rng.x1; q[2] = rng.c0; q[3] = rng.c1;
+        }
+    }
+    if (counters) *counters = cnt;
+    return 0;
 }
 
 static inline void cnt_add(oracle_counters *a, const oracle_counters *b) {
@@ -326,7 +429,8 @@ static inline void cnt_add(oracle_counters *a, const oracle_counters *b) {
 }
 
 int oracle_render(const oracle_job *J, uint8_t *rgba8, float *accum, uint32_t *rng_state, oracle_counters *counters) {
-    if (!J || J->width <= 0 || J->height <= 0 || J->spp <= 0 || J->variant < 0 || J->variant > 3) return -1;
+    if (!J || J->width <= 0 || J->height <= 0 || J->spp <= 0 || J->variant < 0 || J->variant > 4) return -1;
+    if (J->variant == ORACLE_BIDIR && (J->nvpl < 0 || (J->nvpl > 0 && !J->vpls))) return -1;
     if (J->variant == ORACLE_NODOF && J->spp != 64) return -1;
     if (J->variant == ORACLE_GRID && (!J->cell_start || (!J->cell_refs && J->ntriangles > 0))) return -1;
     Scene S;

@@ -8,7 +8,7 @@
  * PARITY PIN: this restatement is pinned against the reference ITSELF — the
  * unmodified reference host .c and kernel .ocl compiled from /root/reference
  * through oracle/refrt (see oracle/Makefile `ref`).  tests/test_oracle_vs_ref.py
- * checks result.ppm byte-equality for all four variants in this container, and
+ * checks result.ppm byte-equality for all five variants in this container, and
  * tests/golden/ holds vectors generated from that reference build (script
  * committed) so the pin travels to machines without /root/reference.
  *
@@ -17,6 +17,8 @@
  *   1 lmem   CLSuperPathTracer_lmem/       running t bound, floor test `r < t`
  *   2 nodof  CLSuperPathTracer_lmem_NoDoF/ lmem semantics, 1 work-item per sample + 8x8 tree reduce
  *   3 grid   CLSuperPathTracer_trianglegrid/ lmem semantics, triangles through the uniform grid (DDA)
+ *   4 bidir  CLSuperBidirectionalPathTracer/ lmem TraceRay; lightTracer kernel deposits virtual point lights
+ *            (VPLs), Sample gathers all of them unshadowed, then SUBTRACTS 1/nlights per occluded real light
  *
  * Arithmetic policy (compile-time PT_CONTRACT):
  *   0  every float operation individually rounded (what g++ makes of the reference .ocl; image bytes
@@ -36,7 +38,7 @@
 extern "C" {
 #endif
 
-enum { ORACLE_BASE = 0, ORACLE_LMEM = 1, ORACLE_NODOF = 2, ORACLE_GRID = 3 };
+enum { ORACLE_BASE = 0, ORACLE_LMEM = 1, ORACLE_NODOF = 2, ORACLE_GRID = 3, ORACLE_BIDIR = 4 };
 
 typedef struct {
     uint64_t samples;        /* Sample() calls                         */
@@ -67,6 +69,9 @@ typedef struct {
     const uint32_t *cell_start; /* ncells+1 offsets into cell_refs */
     const uint32_t *cell_refs;  /* triangle ids, per cell in triangle-id order, <= 62 per cell */
     int32_t nthreads;           /* 0 = OpenMP default */
+    /* bidir variant only: the buffer lightTracer filled, nvpl x (x y z intensity), in buffer order */
+    const float *vpls;
+    int32_t nvpl;
 } oracle_job;
 
 /* Outputs may be NULL.  rgba8: W*H*4 bytes.  accum: W*H*4 floats (the value handed to
@@ -74,6 +79,13 @@ typedef struct {
  * 0,1,3; 64*W*H in the 8W x 8H work-item order for nodof).  Returns 0, or -1 on bad arguments. */
 int oracle_render(const oracle_job *job, uint8_t *rgba8, float *accum, uint32_t *rng_state,
                   oracle_counters *counters);
+
+/* Kernel lightTracer of CLSuperBidirectionalPathTracer/bidirectionalpathtracer.ocl:280-326 for a 1-D range of
+ * n_vlp_per_light work-items (scene, lights and seeds from `job`; its variant/size fields are ignored).
+ * vpl_out: n_vlp_per_light*nlights x 4 floats, entry [gi + l*n_vlp_per_light] as in the reference (:324).
+ * rng_state (optional): final RNG state per work-item.  Returns 0, -1 on bad arguments. */
+int oracle_light_tracer(const oracle_job *job, int n_vlp_per_light, float *vpl_out, uint32_t *rng_state,
+                        oracle_counters *counters);
 
 /* policy this library was built with (0 / 1) */
 int oracle_contract_mode(void);

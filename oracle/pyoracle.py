@@ -14,7 +14,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 BUILD = os.path.join(HERE, "_build")
-VARIANTS = {"base": 0, "lmem": 1, "nodof": 2, "grid": 3}
+VARIANTS = {"base": 0, "lmem": 1, "nodof": 2, "grid": 3, "bidir": 4}
 
 
 def build(force=False):
@@ -49,6 +49,7 @@ class oracle_job(C.Structure):
         ("box_min", C.c_float * 4), ("box_max", C.c_float * 4), ("grid_res", C.c_int32 * 4), ("cell_size", C.c_float * 4),
         ("cell_start", C.POINTER(C.c_uint32)), ("cell_refs", C.POINTER(C.c_uint32)),
         ("nthreads", C.c_int32),
+        ("vpls", C.POINTER(C.c_float)), ("nvpl", C.c_int32),
     ]
 
 
@@ -62,6 +63,8 @@ class OracleLib:
         L = self.lib
         L.oracle_render.restype = C.c_int
         L.oracle_render.argtypes = [C.POINTER(oracle_job), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(oracle_counters)]
+        L.oracle_light_tracer.restype = C.c_int
+        L.oracle_light_tracer.argtypes = [C.POINTER(oracle_job), C.c_int, C.c_void_p, C.c_void_p, C.POINTER(oracle_counters)]
         L.oracle_contract_mode.restype = C.c_int
         L.oracle_randomize_id.restype = C.c_uint32
         L.oracle_randomize_id.argtypes = [C.c_uint32]
@@ -147,14 +150,9 @@ class OracleLib:
                                       tris.ctypes.data_as(C.c_void_p), int(tris.shape[0]))
         return m, tt.value, np.array(n[:], np.float32)
 
-    def render(self, variant, width, height, seeds, scene, spp=64, rows=None, cam=None, grid=None, want_accum=True,
-               want_rng=True, nthreads=0, modifier=3.0):
-        """scene: dict with spheres, squares, triangles (n,12), lights (nl,4) [, box_min, box_max]."""
-        J = oracle_job()
-        J.variant = VARIANTS[variant]
-        J.width, J.height, J.spp = width, height, spp
-        if rows is not None:
-            J.row_begin, J.row_end = rows
+    @staticmethod
+    def _fill_scene(J, seeds, scene):
+        """Scene + seeds part of an oracle_job; returns the arrays that must stay alive while J is used."""
         J.seeds[:] = [int(s) & 0xFFFFFFFF for s in seeds]
         J.spheres[:] = [int(v) for v in scene["spheres"]]
         J.squares[:] = [int(v) for v in scene["squares"]]
@@ -166,6 +164,39 @@ class OracleLib:
         for i in range(J.nlights):
             for k in range(4):
                 J.lights[i][k] = float(lights[i, k])
+        return tris
+
+    def light_tracer(self, seeds, scene, n_vlp=512, want_rng=False):
+        """Kernel lightTracer (bidirectionalpathtracer.ocl:280-326): -> (n_vlp*nlights, 4) float32 VPL buffer."""
+        J = oracle_job()
+        tris = self._fill_scene(J, seeds, scene)
+        vpl = np.zeros((n_vlp * J.nlights, 4), np.float32)
+        rng = np.zeros((n_vlp, 4), np.uint32) if want_rng else None
+        cnt = oracle_counters()
+        rc = self.lib.oracle_light_tracer(C.byref(J), int(n_vlp), vpl.ctypes.data_as(C.c_void_p),
+                                          rng.ctypes.data_as(C.c_void_p) if want_rng else None, C.byref(cnt))
+        del tris
+        if rc:
+            raise ValueError("oracle_light_tracer rejected the job")
+        return (vpl, rng) if want_rng else vpl
+
+    def render(self, variant, width, height, seeds, scene, spp=64, rows=None, cam=None, grid=None, want_accum=True,
+               want_rng=True, nthreads=0, modifier=3.0, vpls=None, n_vlp=512):
+        """scene: dict with spheres, squares, triangles (n,12), lights (nl,4) [, box_min, box_max].
+        bidir: `vpls` (n,4) is the lightTracer buffer; None runs light_tracer(seeds, scene, n_vlp) first, as the
+        reference host does (CLSuperBidirectionalPathTracer.c:370-375: same seeds for both kernels)."""
+        J = oracle_job()
+        J.variant = VARIANTS[variant]
+        J.width, J.height, J.spp = width, height, spp
+        if rows is not None:
+            J.row_begin, J.row_end = rows
+        tris = self._fill_scene(J, seeds, scene)
+        if variant == "bidir":
+            if vpls is None:
+                vpls = self.light_tracer(seeds, scene, n_vlp)
+            vpls = np.ascontiguousarray(vpls, np.float32).reshape(-1, 4)
+            J.vpls = vpls.ctypes.data_as(C.POINTER(C.c_float))
+            J.nvpl = vpls.shape[0]
         cam = cam or self.camera()
         J.cam_up[:] = list(cam["cam_up"]); J.cam_right[:] = list(cam["cam_right"]); J.eye_offset[:] = list(cam["eye_offset"])
         keep = None
@@ -196,4 +227,7 @@ class OracleLib:
         if rc:
             raise ValueError("oracle_render rejected the job")
         del keep
-        return {"image": img, "accum": acc, "rng_state": rng, "counters": cnt.as_dict()}
+        out = {"image": img, "accum": acc, "rng_state": rng, "counters": cnt.as_dict()}
+        if variant == "bidir":
+            out["vpls"] = vpls
+        return out

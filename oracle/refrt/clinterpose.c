@@ -21,6 +21,9 @@ extern const unsigned int ref_kernel_source_len;
 #ifndef SEEDS_ARG
 #error "SEEDS_ARG must be defined"
 #endif
+#ifndef SEEDS_ARG2 /* second kernel of the bidirectional program (lightTracer): its own seeds index */
+#define SEEDS_ARG2 SEEDS_ARG
+#endif
 
 cl_program clCreateProgramWithSource(cl_context ctx, cl_uint count, const char **strings, const size_t *lengths, cl_int *err) {
     typedef cl_program (*fn_t)(cl_context, cl_uint, const char **, const size_t *, cl_int *);
@@ -37,7 +40,7 @@ cl_int clSetKernelArg(cl_kernel k, cl_uint idx, size_t size, const void *value) 
     static fn_t real;
     if (!real) real = (fn_t)dlsym(RTLD_NEXT, "clSetKernelArg");
     const char *env = getenv("PT_SEEDS");
-    if (env && value && idx == SEEDS_ARG && size == 16) {
+    if (env && value && (idx == SEEDS_ARG || idx == SEEDS_ARG2) && size == 16) {
         unsigned long v[4];
         if (sscanf(env, "%lu,%lu,%lu,%lu", &v[0], &v[1], &v[2], &v[3]) == 4) {
             cl_uint s[4] = {(cl_uint)v[0], (cl_uint)v[1], (cl_uint)v[2], (cl_uint)v[3]};

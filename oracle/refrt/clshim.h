@@ -55,6 +55,10 @@ struct vec2 {
     explicit vec2(A a) { x = (T)a; y = (T)a; }
 };
 
+/* 3-component swizzle result (`v.s012`, rewritten to `v.s012()` by ocl2cpp.py) */
+template <class T>
+struct vec3 { T x, y, z; };
+
 template <class T>
 struct alignas(sizeof(T) * 4) vec4 {
     union {
@@ -70,6 +74,9 @@ struct alignas(sizeof(T) * 4) vec4 {
     template <class C, class D, class = typename std::enable_if<is_scalar<C>::value && is_scalar<D>::value>::type>
     vec4(vec2<T> ab, C c, D d) { x = ab.x; y = ab.y; z = (T)c; w = (T)d; }
     vec4(vec2<T> ab, vec2<T> cd) { x = ab.x; y = ab.y; z = cd.x; w = cd.y; }
+    template <class D, class = typename std::enable_if<is_scalar<D>::value>::type>
+    vec4(vec3<T> abc, D d) { x = abc.x; y = abc.y; z = abc.z; w = (T)d; }
+    vec3<T> s012() const { vec3<T> r; r.x = x; r.y = y; r.z = z; return r; }
     template <class A, class = typename std::enable_if<is_scalar<A>::value>::type>
     explicit vec4(A a) { x = (T)a; y = (T)a; z = (T)a; w = (T)a; }
 };

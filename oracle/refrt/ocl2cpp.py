@@ -6,8 +6,9 @@ TEST INFRASTRUCTURE ONLY.  Reads a reference kernel file where it lies (e.g.
 Makefile redirects it into oracle/_ref/gen/, which is git-ignored: reference
 sources are never committed to this repo).
 
-The only transformation is  `(vecN)(a, b, ...)`  ->  `vecN{a, b, ...}`  for the
-vector types the hot-path kernels use.  Brace initialisation keeps the
+The transformations are  `(vecN)(a, b, ...)`  ->  `vecN{a, b, ...}`  for the
+vector types the hot-path kernels use, and the swizzle `.s012` -> `.s012()` (a member
+function of the shim's vec4; the bidirectional kernel uses it).  Brace initialisation keeps the
 left-to-right evaluation order that clang-based OpenCL compilers give the two
 RNG calls inside the float4 literal at pathtracer.ocl:233; a function-call
 rewrite would let g++ evaluate them right-to-left.
@@ -56,7 +57,7 @@ def rewrite(src: str) -> str:
             continue
         out.append(text[i])
         i += 1
-    return "".join(out)
+    return re.sub(r"\.s012\b", ".s012()", "".join(out))
 
 
 if __name__ == "__main__":

@@ -1,12 +1,13 @@
 /*
  * ref_kernels.cpp — compiles ONE reference pathtracer.ocl (selected by
- * -DREF_VARIANT=0..3 and -DREF_OCL_GEN="<generated file>") as host C++ and
+ * -DREF_VARIANT=0..4 and -DREF_OCL_GEN="<generated file>") as host C++ and
  * registers its kernels with refrt.  TEST INFRASTRUCTURE ONLY.
  *
  *   REF_VARIANT 0  CLSuperPathTracer/pathtracer.ocl              (base)
  *   REF_VARIANT 1  CLSuperPathTracer_lmem/pathtracer.ocl         (lmem)
  *   REF_VARIANT 2  CLSuperPathTracer_lmem_NoDoF/pathtracer.ocl   (nodof)
  *   REF_VARIANT 3  CLSuperPathTracer_trianglegrid/pathtracer.ocl (grid)
+ *   REF_VARIANT 4  CLSuperBidirectionalPathTracer/bidirectionalpathtracer.ocl (bidir)
  *
  * REF_OCL_GEN is the reference source with vector literals rewritten by ocl2cpp.py; the Makefile
  * pipes it in ("/dev/stdin"), so no copy of it is written anywhere.  Argument
@@ -15,6 +16,7 @@
  *   lmem  CLSuperPathTracer_lmem/CLSuperPathTracer.c:154-186
  *   nodof CLSuperPathTracer_lmem_NoDoF/CLSuperPathTracer.c:155-187, 207-210
  *   grid  CLSuperPathTracer_trianglegrid/CLSuperPathTracer.c:288-297, 337-374
+ *   bidir CLSuperBidirectionalPathTracer/CLSuperBidirectionalPathTracer.c:154-177 (lightTracer), 200-235 (pathTracer)
  *
  * It also exports a few `ref_probe_*` C functions that call the reference's
  * inline device functions directly (RNG, TraceRay) so that unit-level golden
@@ -94,8 +96,22 @@ const RefKernelDesc ref_kernel_table[] = {{"pathTracer", 19, tramp_pathTracer},
                                           {"initTrianglesGrid", 5, tramp_initgrid},
                                           {"printTrianglesGrid", 1, tramp_printgrid},
                                           {nullptr, 0, nullptr}};
+#elif REF_VARIANT == 4
+static void tramp_pathTracer(const RefLaunch &L) {
+    ocl::pathTracer((uchar4 *)L.mem(0), (const int *)L.mem(1), (const int *)L.mem(2), (const Triangle *)L.mem(3),
+                    L.val<int>(4), (const float4 *)L.mem(5), L.val<int>(6), (const float4 *)L.mem(7), L.val<int>(8),
+                    L.val<float4>(9), L.val<float4>(10), L.val<float4>(11), L.val<float4>(12), seeds_arg(L, 13),
+                    (int *)L.local(14), (int *)L.local(15), (Triangle *)L.local(16), (float4 *)L.local(17));
+}
+static void tramp_lightTracer(const RefLaunch &L) {
+    ocl::lightTracer((const int *)L.mem(0), (const int *)L.mem(1), (const Triangle *)L.mem(2), L.val<int>(3),
+                     (const float4 *)L.mem(4), L.val<int>(5), (float4 *)L.mem(6), seeds_arg(L, 7), (int *)L.local(8),
+                     (int *)L.local(9), (Triangle *)L.local(10), (float4 *)L.local(11));
+}
+const RefKernelDesc ref_kernel_table[] = {
+    {"pathTracer", 18, tramp_pathTracer}, {"lightTracer", 12, tramp_lightTracer}, {nullptr, 0, nullptr}};
 #else
-#error "REF_VARIANT must be 0..3"
+#error "REF_VARIANT must be 0..4"
 #endif
 
 /* ------------------------------------------------------------------ probes */

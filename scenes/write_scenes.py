@@ -22,6 +22,7 @@ VARIANT_DIRS = {
     "lmem": "CLSuperPathTracer_lmem",
     "nodof": "CLSuperPathTracer_lmem_NoDoF",
     "grid": "CLSuperPathTracer_trianglegrid",
+    "bidir": "CLSuperBidirectionalPathTracer",
 }
 
 

@@ -20,11 +20,11 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def scene_dirs(tmp_path_factory):
-    """The four reference scene directories, regenerated from scenes/scene_data.py."""
+    """The five reference scene directories, regenerated from scenes/scene_data.py."""
     import write_scenes
     base = tmp_path_factory.mktemp("scenes")
     out = {}
-    for v in ("base", "lmem", "nodof", "grid"):
+    for v in ("base", "lmem", "nodof", "grid", "bidir"):
         d = str(base / v)
         write_scenes.write_variant(v, d)
         out[v] = d

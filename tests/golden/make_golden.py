@@ -8,6 +8,8 @@ and kernels compiled by `make -C oracle ref` (oracle/refrt).  Only runnable in t
   golden_host.json     what the reference hosts print: camera, counts, bbox, grid size; PAM header bytes
   golden_images.npz    result.ppm of every variant for two seed sets at 512x512: SHA-256 + selected rows
   golden_grid.npz      cell contents (sorted ids) written by the reference's initTrianglesGrid kernel
+  golden_bidir.npz     CLSuperBidirectionalPathTracer: the VPL buffer its lightTracer kernel writes (bit patterns,
+                       several N_VLP), result.ppm SHA-256 + rows, and what the host prints
 """
 import ctypes as C
 import hashlib
@@ -89,7 +91,8 @@ def trace_golden(tmp):
 
 def run_ref(variant, d, w, h, seeds, extra=()):
     env = dict(os.environ, PT_SEEDS=",".join(str(s) for s in seeds))
-    out = subprocess.run([os.path.join(REF, "bin", variant, "CLSuperPathTracer"), str(w), str(h), *extra], cwd=d, env=env,
+    exe = "CLSuperBidirectionalPathTracer" if variant == "bidir" else "CLSuperPathTracer"
+    out = subprocess.run([os.path.join(REF, "bin", variant, exe), str(w), str(h), *extra], cwd=d, env=env,
                          capture_output=True, text=True, check=True).stdout
     raw = open(os.path.join(d, "result.ppm"), "rb").read()
     k = raw.index(b"ENDHDR\n") + 7
@@ -172,12 +175,77 @@ def grid_golden(tmp):
     np.savez_compressed(os.path.join(HERE, "golden_grid.npz"), **out)
 
 
+def ref_light_tracer(L, sc, seeds, n_vlp):
+    """The reference's lightTracer kernel through refrt's CL entry points, argument order of
+    CLSuperBidirectionalPathTracer.c:154-177 -> (n_vlp*nlights, 4) float32."""
+    for fn in ("clCreateKernel", "clCreateBuffer", "clEnqueueMapBuffer"):
+        getattr(L, fn).restype = C.c_void_p
+    err = C.c_int()
+    k = C.c_void_p(L.clCreateKernel(None, b"lightTracer", C.byref(err)))
+    COPY = C.c_uint64(1 << 5)
+
+    def buf(a):
+        return C.c_void_p(L.clCreateBuffer(None, COPY, C.c_size_t(a.nbytes), a.ctypes.data_as(C.c_void_p), C.byref(err)))
+    sph = np.ascontiguousarray(sc["spheres"], np.int32); sq = np.ascontiguousarray(sc["squares"], np.int32)
+    tris = np.ascontiguousarray(sc["triangles"], np.float32); lights = np.ascontiguousarray(sc["lights"], np.float32)
+    nl = lights.shape[0]
+    vpl = np.full((n_vlp * nl, 4), np.nan, np.float32)
+    bs, bq, bt, bl, bv = buf(sph), buf(sq), buf(tris), buf(lights), buf(vpl)
+    ntri = C.c_int32(tris.shape[0]); nlc = C.c_int32(nl); sd = (C.c_uint32 * 4)(*seeds)
+    args = [(8, C.byref(bs)), (8, C.byref(bq)), (8, C.byref(bt)), (4, C.byref(ntri)), (8, C.byref(bl)), (4, C.byref(nlc)),
+            (8, C.byref(bv)), (16, sd), (36, None), (36, None), (48 * tris.shape[0], None), (16 * nl, None)]
+    for i, (size, ptr) in enumerate(args):
+        assert L.clSetKernelArg(k, i, C.c_size_t(size), ptr) == 0
+    gws = (C.c_size_t * 1)(n_vlp)
+    assert L.clEnqueueNDRangeKernel(None, k, 1, None, gws, None, 0, None, None) == 0
+    ptr = L.clEnqueueMapBuffer(None, bv, 1, 1, C.c_size_t(0), C.c_size_t(vpl.nbytes), 0, None, None, C.byref(err))
+    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=(n_vlp * nl, 4)).copy()
+
+
+def bidir_golden(tmp):
+    from oracle.pyoracle import OracleLib
+    o = OracleLib(0)
+    d = os.path.join(tmp, "bidir")
+    write_scenes.write_variant("bidir", d)
+    sc = o.load_scene_dir(d, "bidir")
+    L = lib("bidir")
+    out = {}
+    env_seeds = os.environ.pop("PT_SEEDS", None)     # the probe passes its seeds as the kernel argument
+    for si, seeds in enumerate(SEED_SETS):
+        # 512: the default; 700: total/512 truncates to 2; 96: total/512 == 0 -> inf / NaN intensities
+        for n_vlp in (512, 700, 96):
+            out["vpl_s%d_n%d" % (si, n_vlp)] = ref_light_tracer(L, sc, seeds, n_vlp).view(np.uint32)
+    if env_seeds is not None:
+        os.environ["PT_SEEDS"] = env_seeds
+    host = {}
+    for si, seeds in enumerate(SEED_SETS):
+        log, hdr, img = run_ref("bidir", d, 512, 512, seeds)
+        out["img_s%d_sha256" % si] = np.frombuffer(hashlib.sha256(img.tobytes()).digest(), np.uint8)
+        out["img_s%d_rows" % si] = img[ROWS].copy()
+    cam = re.search(r"Cam values:\n(.*\n.*\n.*\n.*)\n", log).group(1)
+    host["bidir"] = {"camera_print": cam, "ntriangles": int(re.search(r"Number of triangles: (\d+)", log).group(1)),
+                     "nlights": int(re.search(r"Number of lights: (\d+)", log).group(1)), "pam_header": hdr.decode(),
+                     "vpl_print": re.search(r"virtual light sampling : (\d+) virtual lights", log).group(1)}
+    for n_vlp, size in ((700, (320, 256)), (96, (256, 256))):
+        log, hdr, img = run_ref("bidir", d, size[0], size[1], SEED_SETS[0], extra=(str(n_vlp),))
+        out["img_n%d_sha256" % n_vlp] = np.frombuffer(hashlib.sha256(img.tobytes()).digest(), np.uint8)
+        out["img_n%d" % n_vlp] = img.copy() if n_vlp == 96 else img[[100, 180, 255]].copy()
+        out["img_n%d_size" % n_vlp] = np.array(size)
+    out["rows"] = np.array(ROWS)
+    out["host_json"] = np.frombuffer(json.dumps(host).encode(), np.uint8)
+    np.savez_compressed(os.path.join(HERE, "golden_bidir.npz"), **out)
+
+
 if __name__ == "__main__":
     sys.path.insert(0, ROOT)
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref", "oracle"])
     with tempfile.TemporaryDirectory() as tmp:
+        if sys.argv[1:] == ["bidir"]:
+            bidir_golden(tmp)
+            sys.exit(0)
         rng_golden()
         trace_golden(tmp)
         images_and_host(tmp)
         grid_golden(tmp)
+        bidir_golden(tmp)
     print("golden vectors written to", HERE)

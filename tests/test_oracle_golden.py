@@ -135,3 +135,43 @@ def test_contract_modes_agree_within_tolerance(oracle_sep, oracle_fma, scene_dir
     assert (diff <= 1).mean() >= 0.995 and np.sqrt((diff.astype(float) ** 2).mean()) <= 0.5
     rel = np.abs(a["accum"] - b["accum"])[rows[0]:rows[1]][same_rng] / np.maximum(np.abs(a["accum"][rows[0]:rows[1]][same_rng]), 1e-6)
     assert np.median(rel) <= 1e-6
+
+
+# ---- CLSuperBidirectionalPathTracer --------------------------------------------------
+def test_bidir_light_tracer_golden(oracle_sep, scene_dirs):
+    """The VPL buffer of the reference's lightTracer kernel, bit for bit — including N_VLP*nlights < 512,
+    where the reference divides by (total_vlp/512) == 0 and deposits inf / NaN intensities."""
+    g = np.load(os.path.join(G, "golden_bidir.npz"))
+    sc = oracle_sep.load_scene_dir(scene_dirs["bidir"], "bidir")
+    for si, seeds in enumerate(SEED_SETS):
+        for n in (512, 700, 96):
+            got = oracle_sep.light_tracer(seeds, sc, n)
+            ref = g["vpl_s%d_n%d" % (si, n)]
+            assert np.array_equal(got.view(np.uint32), ref), (si, n)
+    f = g["vpl_s0_n96"].view(np.float32)[:, 3]
+    assert np.isnan(f).any() and np.isinf(f).any()
+    # only surfaces hit from BEHIND keep a non-zero intensity (the reference dots the incoming direction with the
+    # outward normal): every non-zero VPL of the default scene lies on a square (z = 4, 10 or 12)
+    v = g["vpl_s0_n512"].view(np.float32)
+    z = v[v[:, 3] != 0][:, 2]
+    assert np.abs(z[:, None] - np.array([4.0, 10.0, 12.0])[None]).min(axis=1).max() < 1e-5
+
+
+def test_bidir_image_golden(oracle_sep, scene_dirs):
+    g = np.load(os.path.join(G, "golden_bidir.npz"))
+    sc = oracle_sep.load_scene_dir(scene_dirs["bidir"], "bidir")
+    out = oracle_sep.render("bidir", 512, 512, SEED_SETS[0], sc, want_rng=False, want_accum=False)
+    assert hashlib.sha256(out["image"].tobytes()).digest() == g["img_s0_sha256"].tobytes()
+    for ri, row in enumerate(g["rows"]):
+        o2 = oracle_sep.render("bidir", 512, 512, SEED_SETS[1], sc, rows=(int(row), int(row) + 1), want_rng=False)
+        assert np.array_equal(o2["image"][row], g["img_s1_rows"][ri]), int(row)
+    # N_VLP given on the command line (argv[3]): 700 and the degenerate 96
+    w, h = (int(x) for x in g["img_n700_size"])
+    out = oracle_sep.render("bidir", w, h, SEED_SETS[0], sc, n_vlp=700, want_rng=False, want_accum=False)
+    assert hashlib.sha256(out["image"].tobytes()).digest() == g["img_n700_sha256"].tobytes()
+    w, h = (int(x) for x in g["img_n96_size"])
+    out = oracle_sep.render("bidir", w, h, SEED_SETS[0], sc, n_vlp=96, want_rng=False, want_accum=False)
+    assert np.array_equal(out["image"], g["img_n96"])
+    host = json.loads(bytes(g["host_json"]).decode())["bidir"]
+    assert sc["triangles"].shape[0] == host["ntriangles"] and sc["lights"].shape[0] == host["nlights"]
+    assert int(host["vpl_print"]) == 512 * host["nlights"]

@@ -19,13 +19,15 @@ def test_scene_files_regenerate_byte_identical():
 
 
 @pytest.mark.skipif(not have_ref, reason="needs oracle/_ref (make -C oracle ref)")
-@pytest.mark.parametrize("variant,size", [("base", (256, 384)), ("lmem", (256, 384)), ("nodof", (256, 384)), ("grid", (256, 384))])
+@pytest.mark.parametrize("variant,size", [("base", (256, 384)), ("lmem", (256, 384)), ("nodof", (256, 384)), ("grid", (256, 384)),
+                                          ("bidir", (320, 384))])
 def test_result_ppm_identical(oracle_sep, scene_dirs, tmp_path, variant, size):
     """Unmodified reference host + kernel (CPU, refrt) vs oracle_render: identical result.ppm bytes."""
     w, h = size
     d = scene_dirs[variant]
     env = dict(os.environ, PT_SEEDS=",".join(str(s) for s in SEED_SETS[1]))
-    subprocess.run([os.path.join(REF_BUILD, "bin", variant, "CLSuperPathTracer"), str(w), str(h)], cwd=d, env=env, check=True,
+    exe = "CLSuperBidirectionalPathTracer" if variant == "bidir" else "CLSuperPathTracer"
+    subprocess.run([os.path.join(REF_BUILD, "bin", variant, exe), str(w), str(h)], cwd=d, env=env, check=True,
                    capture_output=True)
     raw = open(os.path.join(d, "result.ppm"), "rb").read()
     k = raw.index(b"ENDHDR\n") + 7
