@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_DIR = os.path.join(_HERE, "lib")
 BIN_DIR = os.path.join(_HERE, "bin")
 
-PT_VARIANT = {"base": 0, "lmem": 1, "nodof": 2, "grid": 3}
+PT_VARIANT = {"base": 0, "lmem": 1, "nodof": 2, "grid": 3, "bidir": 4}
 PT_KERNEL = {"mega": 0, "persistent": 1, "wavefront": 2, "auto": 3, "grid_tma": 4}
 PT_SCENE_MEM = {"const": 0, "smem": 1, "auto": 2}
 PT_ARITH = {"separate": 0, "fma": 1}
@@ -65,6 +65,7 @@ class pt_render_params(C.Structure):
         ("rank", C.c_int32),
         ("nranks", C.c_int32),
         ("no_cull", C.c_int32),
+        ("n_vlp", C.c_int32),
     ]
 
 
@@ -77,6 +78,7 @@ class pt_counters(C.Structure):
         ("cells_visited", C.c_uint64),
         ("prim_tests", C.c_uint64),
         ("tri_tests_executed", C.c_uint64),
+        ("vpl_evals", C.c_uint64),
     ]
 
     def as_dict(self):
@@ -108,6 +110,9 @@ PTCUDA_SYMBOLS = {
     "pt_read_accum": (_I, [_VP, _FP, C.c_size_t]),
     "pt_read_rng_state": (_I, [_VP, _U32P, C.c_size_t]),
     "pt_get_counters": (_I, [_VP, C.POINTER(pt_counters)]),
+    "pt_launch_lighttracer": (_VP, [_VP, _I, _U32P, _I]),
+    "pt_set_vpls": (_I, [_VP, _FP, _I]),
+    "pt_read_vpls": (_I, [_VP, _FP, _I]),
     "pt_render_device": (_I, [_VP, C.POINTER(pt_camera), C.POINTER(pt_render_params), _VP, _VP]),
     "pt_tonemap_device": (_I, [_VP, _VP, _VP, _I, _I]),
     "pt_render_host": (_I, [_VP, C.POINTER(pt_scene), C.POINTER(pt_grid), C.POINTER(pt_camera),
@@ -116,6 +121,7 @@ PTCUDA_SYMBOLS = {
     "pt_multi_destroy": (None, [_VP]),
     "pt_multi_set_scene": (_I, [_VP, C.POINTER(pt_scene)]),
     "pt_multi_build_grid": (_VP, [_VP, C.POINTER(pt_grid)]),
+    "pt_multi_launch_lighttracer": (_VP, [_VP, _I, _U32P, _I]),
     "pt_multi_launch_pathtracer": (_VP, [_VP, C.POINTER(pt_camera), C.POINTER(pt_render_params)]),
     "pt_multi_map_render": (_VP, [_VP, C.POINTER(_VP)]),
     "pt_multi_get_counters": (_I, [_VP, C.POINTER(pt_counters)]),

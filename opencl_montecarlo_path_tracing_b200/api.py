@@ -125,7 +125,7 @@ class RenderResult:
 
 
 def make_params(variant, width, height, seeds, spp=64, kernel="auto", scene_mem=None, arith="fma", rows=None,
-                want_accum=False, want_rng=False, interleave=0, rank=0, nranks=1, cull=True):
+                want_accum=False, want_rng=False, interleave=0, rank=0, nranks=1, cull=True, n_vlp=0):
     p = pt_render_params()
     p.variant = PT_VARIANT[variant]
     p.width, p.height, p.spp = int(width), int(height), int(spp)
@@ -140,6 +140,7 @@ def make_params(variant, width, height, seeds, spp=64, kernel="auto", scene_mem=
     p.want_accum, p.want_rng = int(bool(want_accum)), int(bool(want_rng))
     p.row_interleave, p.rank, p.nranks = int(interleave), int(rank), int(nranks)
     p.no_cull = 0 if cull else 1
+    p.n_vlp = int(n_vlp)
     return p
 
 
@@ -206,6 +207,32 @@ class Renderer:
         raw = np.zeros(ncells * 128, np.uint8)
         _check(self._l.pt_read_grid_cells(self.ctx, raw.ctypes.data_as(C.c_void_p), ncells), "pt_read_grid_cells")
         return raw.reshape(ncells, 128)
+
+    # ---- bidirectional variant (CLSuperBidirectionalPathTracer): virtual point lights ----
+    def light_tracer(self, seeds, n_vlp=512, arith="fma"):
+        """Kernel lightTracer (CLSuperBidirectionalPathTracer.c:143-184): fills the context's VPL buffer, which the next
+        variant="bidir" render gathers.  Returns the device time in ms."""
+        s = (C.c_uint32 * 4)(*[int(v) & 0xFFFFFFFF for v in seeds])
+        evt = self._l.pt_launch_lighttracer(self.ctx, int(n_vlp), s, PT_ARITH[arith])
+        if not evt:
+            raise PtError("pt_launch_lighttracer failed: %s" % self._l.pt_last_error().decode())
+        _check(self._l.pt_wait(evt), "pt_wait")
+        ms = self._l.pt_runtime_ms(evt)
+        self._l.pt_release_event(evt)
+        return ms
+
+    def set_vpls(self, vpls):
+        v = np.ascontiguousarray(vpls, np.float32).reshape(-1, 4)
+        _check(self._l.pt_set_vpls(self.ctx, v.ctypes.data_as(C.POINTER(C.c_float)), v.shape[0]), "pt_set_vpls")
+
+    def read_vpls(self):
+        n = self._l.pt_read_vpls(self.ctx, None, 0)
+        if n < 0:
+            raise PtError("pt_read_vpls failed: %s" % self._l.pt_last_error().decode())
+        v = np.zeros((max(n, 1), 4), np.float32)
+        if self._l.pt_read_vpls(self.ctx, v.ctypes.data_as(C.POINTER(C.c_float)), max(n, 1)) < 0:
+            raise PtError("pt_read_vpls failed: %s" % self._l.pt_last_error().decode())
+        return v[:n]
 
     def render(self, variant, width, height, seeds, read_image=True, **kw):
         p = make_params(variant, width, height, seeds, **kw)

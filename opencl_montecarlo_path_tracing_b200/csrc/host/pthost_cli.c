@@ -1,11 +1,12 @@
 /*
  * pthost_cli.c — the drop-in command-line programs.  One driver, parameterised by variant, reproduces
  * the argv, the scene files read from the current directory, the stdout lines (in order) and the
- * result.ppm of the four reference mains:
+ * result.ppm of the reference mains:
  *   CLSuperPathTracer/CLSuperPathTracer.c:186-339            (PT_VARIANT_BASE)
  *   CLSuperPathTracer_lmem/CLSuperPathTracer.c:195-354       (PT_VARIANT_LMEM)
  *   CLSuperPathTracer_lmem_NoDoF/CLSuperPathTracer.c:219-394 (PT_VARIANT_NODOF)
  *   CLSuperPathTracer_trianglegrid/CLSuperPathTracer.c:383-583 (PT_VARIANT_GRID)
+ *   CLSuperBidirectionalPathTracer/CLSuperBidirectionalPathTracer.c:245-422 (PT_VARIANT_BIDIR; argv[3] = N_VLP per light)
  * Where the reference talks to OpenCL through ocl_boiler.h, this talks to libptcuda.so (ptcuda.h).
  *
  * Extensions are env-only so the command line stays a drop-in:
@@ -40,18 +41,22 @@ static int env_choice(const char *name, const char *const *opts, int nopts, int 
 int pth_cli_main(int variant, int argc, char **argv) {
     int img_width = 512, img_height = 512;
     float cell_size_modifier = 3.0f;
-    const int grid = variant == PT_VARIANT_GRID, nodof = variant == PT_VARIANT_NODOF;
+    const int grid = variant == PT_VARIANT_GRID, nodof = variant == PT_VARIANT_NODOF, bidir = variant == PT_VARIANT_BIDIR;
     const int samples_per_pixel_nodof = 64;
+    int n_vlp = 512;
 
     if (grid)
         printf("Usage: %s [img_width] [img_height] [CELL_SIZE_MODIFIER]\nLoads data from triangles.txt, lights.txt, spheres.txt and squares.txt\n", argv[0]);
     else if (nodof)
         printf("Usage: %s [img_width] [img_height]\nLoads data from triangles.txt, lights.txt, spheres.txt and planes.txt", argv[0]);
+    else if (bidir)
+        printf("Usage: %s [img_width] [img_height] [N_VLP_per_light]\nLoads data from triangles.txt, lights.txt, spheres.txt and squares.txt\n", argv[0]);
     else
         printf("Usage: %s [img_width] [img_height]\nLoads data from triangles.txt, lights.txt, spheres.txt and squares.txt\n", argv[0]);
     if (argc > 1) img_width = atoi(argv[1]);
     if (argc > 2) img_height = atoi(argv[2]);
     if (grid && argc > 3) cell_size_modifier = (float)atof(argv[3]);
+    if (bidir && argc > 3) n_vlp = atoi(argv[3]);
 
     /* select_platform / select_device / create_* of ocl_boiler.h */
     printf("number of platforms: %u\n", 1u);
@@ -61,7 +66,7 @@ int pth_cli_main(int variant, int argc, char **argv) {
     pt_multi multi = ngpus > 1 ? pt_multi_create(ngpus) : NULL;
     pt_ctx ctx = multi ? NULL : pt_create(dev);
     time_t now = time(NULL);
-    printf("compiling:\n// %s#include \"%s\"\n", ctime(&now), "pathtracer.ocl");
+    printf("compiling:\n// %s#include \"%s\"\n", ctime(&now), bidir ? "bidirectionalpathtracer.ocl" : "pathtracer.ocl");
     printf("=== BUILD LOG ===\n%s\n=========\n", "kernels are precompiled CUDA for sm_100a (libptcuda.so); nothing to build\n");
 
     uint32_t seeds[4];
@@ -104,7 +109,7 @@ int pth_cli_main(int variant, int argc, char **argv) {
         pth_grid_dims(box_min, box_max, scene.ntriangles, cell_size_modifier, &gdesc);
         printf("Triangles grid size: %d x %d x %d\n", gdesc.res[0], gdesc.res[1], gdesc.res[2]);
     }
-    scene.nlights = pth_parse_lights("lights.txt", scene.lights, variant != PT_VARIANT_BASE);
+    scene.nlights = pth_parse_lights("lights.txt", scene.lights, variant != PT_VARIANT_BASE && !bidir);   /* base and bidir do not echo the lights */
     if (scene.nlights < 0) pt_check(1, "open lights.txt");
     printf("Number of triangles: %d\n", scene.ntriangles);
     printf("Number of lights: %d\n", scene.nlights);
@@ -128,6 +133,13 @@ int pth_cli_main(int variant, int argc, char **argv) {
     rp.arith = env_choice("PT_ARITH", ariths, 2, PT_ARITH_FMA);
     rp.no_cull = getenv("PT_NO_CULL") ? atoi(getenv("PT_NO_CULL")) : 0;
 
+    pt_event light_evt = NULL;
+    if (bidir && !getenv("PT_NO_WARMUP")) {     /* untimed first light pass (lazy module load), also feeds the warm-up render */
+        pt_event w = multi ? pt_multi_launch_lighttracer(multi, n_vlp, seeds, rp.arith) : pt_launch_lighttracer(ctx, n_vlp, seeds, rp.arith);
+        pt_wait(w);
+        pt_release_event(w);
+    } else if (bidir)
+        light_evt = multi ? pt_multi_launch_lighttracer(multi, n_vlp, seeds, rp.arith) : pt_launch_lighttracer(ctx, n_vlp, seeds, rp.arith);
     if (!getenv("PT_NO_WARMUP")) {
         /* One untimed single-row launch first: CUDA loads kernel code lazily (and NCCL sets up its rings) on first
          * use, which the reference's OpenCL event times never include (its JIT runs in clBuildProgram). */
@@ -138,6 +150,8 @@ int pth_cli_main(int variant, int argc, char **argv) {
         pt_wait(w);
         pt_release_event(w);
     }
+    if (bidir && !light_evt)
+        light_evt = multi ? pt_multi_launch_lighttracer(multi, n_vlp, seeds, rp.arith) : pt_launch_lighttracer(ctx, n_vlp, seeds, rp.arith);
     pt_event render_evt = multi ? pt_multi_launch_pathtracer(multi, &cam, &rp) : pt_launch_pathtracer(ctx, &cam, &rp);
     pt_event read_evt = NULL;
     void *pixels = multi ? pt_multi_map_render(multi, &read_evt) : pt_map_render(ctx, &read_evt);
@@ -149,7 +163,12 @@ int pth_cli_main(int variant, int argc, char **argv) {
     } else
         printf("\nSuccessfully created render image %s in the current directory\n\n", image_name);
 
-    double render_ms = pt_runtime_ms(render_evt), read_ms = pt_runtime_ms(read_evt);
+    double render_ms = pt_runtime_ms(render_evt), read_ms = pt_runtime_ms(read_evt), light_ms = 0.0;
+    if (bidir) {
+        light_ms = pt_runtime_ms(light_evt);
+        printf("virtual light sampling : %d virtual lights in %gms: %g GB/s\n", n_vlp * scene.nlights, light_ms,
+               n_vlp * scene.nlights * 16 / 1.0e6 / light_ms);
+    }
     if (grid) {
         double grid_ms = pt_runtime_ms(grid_evt);
         size_t grid_bytes = (size_t)128 * gdesc.res[0] * gdesc.res[1] * gdesc.res[2];
@@ -165,7 +184,7 @@ int pth_cli_main(int variant, int argc, char **argv) {
     } else
         printf("rendering : %d pixels in %gms: %g GB/s\n", img_width * img_height, render_ms, data_size / 1.0e6 / render_ms);
     printf("read render data : %ld uchar in %gms: %g GB/s\n", data_size, read_ms, data_size / 1.0e6 / read_ms);
-    printf("\nTotal time: %g ms.\n", render_ms + read_ms);
+    printf("\nTotal time: %g ms.\n", light_ms + render_ms + read_ms);
 
     if (getenv("PT_STATS")) {
         pt_counters c;
@@ -182,6 +201,7 @@ int pth_cli_main(int variant, int argc, char **argv) {
     pt_release_event(render_evt);
     pt_release_event(read_evt);
     pt_release_event(grid_evt);
+    pt_release_event(light_evt);
     free(tris);
     if (multi) pt_multi_destroy(multi); else pt_destroy(ctx);
     return 0;

@@ -25,6 +25,8 @@ struct LaunchArgs {
     const SceneBlock *gscene;      // global-memory copy of the scene block (shared-memory staging source)
     int scene_bytes;               // bytes of the block actually used (header + prims + ntri records)
     uint32_t scatter_mul;          // persistent kernel: work item w -> (w * scatter_mul) % nitems (0 = identity)
+    const float4 *vpl;             // bidirectional variant: non-zero VPLs, dense, in buffer order
+    const int *nvpl_active;        //   their number (device memory: written by k_compact_vpls)
 };
 
 // virtual row -> image row (identity, or the rank's interleaved stripes)
@@ -81,6 +83,13 @@ struct pt_ctx_s {
     int last_w, last_h, last_variant;
     size_t last_rng_items;
 
+    // bidirectional variant: VPL buffer as the reference defines it + its compacted non-zero entries
+    bool vpls_set;
+    int nvpl;                     // entries of d_vpls (n_vlp_per_light * nlights)
+    float4 *d_vpls, *d_vpl_active;
+    int *d_vpl_count;
+    size_t vpls_cap;              // entries allocated
+
     // wavefront / persistent scratch
     void *d_scratch;
     size_t scratch_cap;
@@ -110,3 +119,6 @@ int pt_launch_persistent(pt_ctx ctx, const pt_render_params *p, const pt::Launch
 int pt_launch_wavefront(pt_ctx ctx, const pt_render_params *p, const pt::LaunchArgs &args);
 int pt_launch_grid_tma(pt_ctx ctx, const pt_render_params *p, const pt::LaunchArgs &args);
 int pt_grid_build_device(pt_ctx ctx, const pt_grid *g);
+int pt_launch_bidir(pt_ctx ctx, const pt_render_params *p, const pt::LaunchArgs &args);
+int pt_launch_light_tracer_kernels(pt_ctx ctx, int arith, const pt::LaunchArgs &args, int n, float4 *vpl, uint4 *rng_out,
+                                   float4 *active, int *count);

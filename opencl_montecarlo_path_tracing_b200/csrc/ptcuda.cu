@@ -19,6 +19,7 @@
 #include "pt_wavefront.cuh"
 #include "pt_gridbuild.cuh"
 #include "pt_gridtma.cuh"
+#include "pt_bidir.cuh"
 
 // ------------------------------------------------------------------------------------ errors
 static int g_error_mode = PT_ERRORS_EXIT;
@@ -130,6 +131,7 @@ extern "C" void pt_destroy(pt_ctx c) {
     cudaFree(c->d_tris_raw);
     cudaFree(c->d_cells); cudaFree(c->d_recs); cudaFree(c->d_refs); cudaFree(c->d_cell_start);
     cudaFree(c->d_rgba); cudaFree(c->d_accum); cudaFree(c->d_rng); cudaFree(c->d_counters); cudaFree(c->d_scratch);
+    cudaFree(c->d_vpls); cudaFree(c->d_vpl_active); cudaFree(c->d_vpl_count);
     if (c->h_rgba) cudaFreeHost(c->h_rgba);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     free(c);
@@ -411,7 +413,9 @@ static int ensure_dev(void **p, size_t *cap, size_t bytes) {
 
 static int validate_params(pt_ctx c, const pt_render_params *p) {
     if (!c->scene_set) return pt_fail(1, "render: call pt_set_scene first");
-    if (p->variant < 0 || p->variant > 3) return pt_fail(1, "render: unknown variant %d", p->variant);
+    if (p->variant < 0 || p->variant > PT_VARIANT_BIDIR) return pt_fail(1, "render: unknown variant %d", p->variant);
+    if (p->variant == PT_VARIANT_BIDIR && !c->vpls_set)
+        return pt_fail(1, "render: the bidirectional variant needs pt_launch_lighttracer (or pt_set_vpls) first");
     if (p->width <= 0 || p->height <= 0) return pt_fail(1, "render: bad image size %dx%d", p->width, p->height);
     if (p->spp <= 0) return pt_fail(1, "render: spp must be positive");
     if (p->variant == PT_VARIANT_NODOF && p->spp != 64) return pt_fail(1, "render: the NoDoF variant is defined for 64 samples (8x8 work-items) per pixel");
@@ -479,6 +483,7 @@ static int fill_args(pt_ctx c, const pt_camera *cam, const pt_render_params *p, 
     }
     A->ap.ntri_hint = p->variant == PT_VARIANT_GRID ? 0 : hs->ntri;
     A->ap.tri_coop = 0;    // set by the launchers that stage the records in shared memory
+    A->vpl = c->d_vpl_active; A->nvpl_active = c->d_vpl_count;
     return 0;
 }
 
@@ -486,7 +491,8 @@ static int fill_args(pt_ctx c, const pt_camera *cam, const pt_render_params *p, 
 static pt_render_params resolve_auto(const pt_render_params *in) {
     pt_render_params p = *in;
     if (p.kernel == PT_KERNEL_AUTO) {
-        if (p.variant == PT_VARIANT_NODOF) p.kernel = PT_KERNEL_PERSISTENT;
+        if (p.variant == PT_VARIANT_BIDIR) p.kernel = PT_KERNEL_MEGA;
+        else if (p.variant == PT_VARIANT_NODOF) p.kernel = PT_KERNEL_PERSISTENT;
         else if (p.variant == PT_VARIANT_GRID) p.kernel = PT_KERNEL_MEGA;
         else {
             // brute-force triangle scenes: a pixel that sees the mesh is a ~1.7 ms serial chain at 64 spp.  Small
@@ -506,6 +512,10 @@ static int dispatch(pt_ctx c, const pt_render_params *pin, const pt::LaunchArgs 
     const pt_render_params *p = &resolved;
     PT_CUDA(cudaMemsetAsync(c->d_counters, 0, 8 * sizeof(unsigned long long), c->stream), "clear counters");
     if (A.nrows <= 0) return 0;
+    if (p->variant == PT_VARIANT_BIDIR) {
+        if (p->kernel != PT_KERNEL_MEGA) return pt_fail(1, "render: the bidirectional variant has the megakernel flavour only (PT_KERNEL_MEGA / AUTO)");
+        return pt_launch_bidir(c, p, A);
+    }
     switch (p->kernel) {
         case PT_KERNEL_MEGA: return pt_launch_mega(c, p, A);
         case PT_KERNEL_PERSISTENT: return pt_launch_persistent(c, p, A);
@@ -542,6 +552,76 @@ extern "C" pt_event pt_launch_pathtracer(pt_ctx c, const pt_camera *cam, const p
     return e;
 }
 
+// ------------------------------------------------------------------------------- bidirectional: VPLs
+static int ensure_vpls(pt_ctx c, int n) {
+    if (!c->d_vpl_count) PT_CUDA(cudaMalloc(&c->d_vpl_count, sizeof(int)), "alloc VPL count");
+    const size_t need = n > 0 ? (size_t)n : 1;
+    if (c->vpls_cap >= need) return 0;
+    cudaFree(c->d_vpls); cudaFree(c->d_vpl_active);
+    c->d_vpls = c->d_vpl_active = nullptr;
+    c->vpls_cap = 0;
+    PT_CUDA(cudaMalloc(&c->d_vpls, need * sizeof(float4)), "alloc VPL buffer");
+    PT_CUDA(cudaMalloc(&c->d_vpl_active, need * sizeof(float4)), "alloc VPL list");
+    c->vpls_cap = need;
+    return 0;
+}
+
+extern "C" pt_event pt_launch_lighttracer(pt_ctx c, int n_vlp_per_light, const uint32_t seeds[4], int arith) {
+    if (!c || !seeds) { pt_fail(1, "pt_launch_lighttracer: null argument"); return nullptr; }
+    if (!c->scene_set) { pt_fail(1, "pt_launch_lighttracer: call pt_set_scene first"); return nullptr; }
+    if (n_vlp_per_light <= 0 || (long long)n_vlp_per_light * 5 > 0x7fffffffLL) { pt_fail(1, "pt_launch_lighttracer: bad N_VLP %d", n_vlp_per_light); return nullptr; }
+    PT_CUDA_NULL(cudaSetDevice(c->device), "select device");
+    const int ar = arith != PT_ARITH_SEPARATE ? PT_ARITH_FMA : PT_ARITH_SEPARATE;
+    const int nl = c->h_scene[ar]->nlights;
+    if (ensure_vpls(c, n_vlp_per_light * nl)) return nullptr;
+    pt_camera cam0;
+    memset(&cam0, 0, sizeof(cam0));
+    pt_render_params rp0;
+    memset(&rp0, 0, sizeof(rp0));
+    rp0.variant = PT_VARIANT_LMEM; rp0.width = 1; rp0.height = 1; rp0.spp = 64; rp0.arith = ar;
+    memcpy(rp0.seeds, seeds, sizeof(rp0.seeds));
+    pt::LaunchArgs LA;
+    fill_args(c, &cam0, &rp0, nullptr, nullptr, nullptr, &LA);
+    pt_event e = event_new(c);
+    if (!e) return nullptr;
+    cudaEventRecord(e->start, c->stream);
+    if (pt_launch_light_tracer_kernels(c, ar, LA, n_vlp_per_light, c->d_vpls, nullptr, c->d_vpl_active, c->d_vpl_count)) {
+        pt_release_event(e);
+        return nullptr;
+    }
+    cudaEventRecord(e->stop, c->stream);
+    c->nvpl = n_vlp_per_light * nl;
+    c->vpls_set = true;
+    return e;
+}
+
+extern "C" int pt_set_vpls(pt_ctx c, const float *vpls, int n) {
+    if (!c || n < 0 || (n > 0 && !vpls)) return pt_fail(1, "pt_set_vpls: bad argument");
+    PT_CUDA(cudaSetDevice(c->device), "select device");
+    int rc = ensure_vpls(c, n);
+    if (rc) return rc;
+    if (n > 0) PT_CUDA(cudaMemcpyAsync(c->d_vpls, vpls, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, c->stream), "upload VPLs");
+    pt::k_compact_vpls<<<1, 256, 0, c->stream>>>(c->d_vpls, n, c->d_vpl_active, c->d_vpl_count);
+    PT_CUDA(cudaGetLastError(), "launch k_compact_vpls");
+    PT_CUDA(cudaStreamSynchronize(c->stream), "sync VPL upload");     // the host buffer may be pageable
+    c->nvpl = n;
+    c->vpls_set = true;
+    return 0;
+}
+
+extern "C" int pt_read_vpls(pt_ctx c, float *vpls, int capacity) {
+    if (!c || !c->vpls_set) { pt_fail(1, "pt_read_vpls: no VPL buffer (pt_launch_lighttracer / pt_set_vpls first)"); return -1; }
+    if (!vpls) return c->nvpl;
+    if (capacity < c->nvpl) { pt_fail(1, "pt_read_vpls: buffer too small (%d < %d)", capacity, c->nvpl); return -1; }
+    if (cudaSetDevice(c->device) != cudaSuccess) { pt_fail(1, "select device"); return -1; }
+    if (c->nvpl > 0 && cudaMemcpyAsync(vpls, c->d_vpls, (size_t)c->nvpl * sizeof(float4), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) {
+        pt_fail(1, "read VPLs");
+        return -1;
+    }
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { pt_fail(1, "sync"); return -1; }
+    return c->nvpl;
+}
+
 extern "C" int pt_render_device(pt_ctx c, const pt_camera *cam, const pt_render_params *p, void *d_rgba8, void *d_accum_f32) {
     if (!c || !cam || !p || !d_rgba8) return pt_fail(1, "pt_render_device: null argument");
     int rc = validate_params(c, p);
@@ -549,6 +629,7 @@ extern "C" int pt_render_device(pt_ctx c, const pt_camera *cam, const pt_render_
     PT_CUDA(cudaSetDevice(c->device), "select device");
     pt::LaunchArgs A;
     fill_args(c, cam, p, (uint32_t *)d_rgba8, (float4 *)d_accum_f32, nullptr, &A);
+    c->last_variant = p->variant;
     return dispatch(c, p, A);
 }
 
@@ -595,6 +676,9 @@ extern "C" int pt_get_counters(pt_ctx c, pt_counters *out) {
     PT_CUDA(cudaStreamSynchronize(c->stream), "sync");
     out->samples = h[0]; out->rays = h[1]; out->shadow_rays = h[2]; out->tri_tests = h[3];
     out->cells_visited = h[4]; out->prim_tests = h[5]; out->tri_tests_executed = h[6];
+    out->vpl_evals = 0;
+    if (c->last_variant == PT_VARIANT_BIDIR && c->scene_set && c->h_scene[1]->nlights > 0)   // nlights shadow rays per hit sample
+        out->vpl_evals = h[2] / (uint64_t)c->h_scene[1]->nlights * (uint64_t)c->nvpl;
     return 0;
 }
 
@@ -703,6 +787,11 @@ extern "C" int pt_render_host(pt_ctx c, const pt_scene *scene, const pt_grid *gr
         if (!g) return 1;
         pt_release_event(g);
     }
+    if (p->variant == PT_VARIANT_BIDIR) {
+        pt_event l = pt_launch_lighttracer(c, p->n_vlp > 0 ? p->n_vlp : 512, p->seeds, p->arith);
+        if (!l) return 1;
+        pt_release_event(l);
+    }
     pt_event e = pt_launch_pathtracer(c, cam, p);
     if (!e) return 1;
     void *h = pt_map_render(c, nullptr);
@@ -807,6 +896,17 @@ extern "C" pt_event pt_multi_build_grid(pt_multi m, const pt_grid *grid) {
     return first;
 }
 
+// every device traces the (tiny) light pass itself: identical seeds -> identical VPL buffers, no exchange needed
+extern "C" pt_event pt_multi_launch_lighttracer(pt_multi m, int n_vlp_per_light, const uint32_t seeds[4], int arith) {
+    pt_event first = nullptr;
+    for (int i = 0; i < m->n; ++i) {
+        pt_event e = pt_launch_lighttracer(m->ctx[i], n_vlp_per_light, seeds, arith);
+        if (!e) return nullptr;
+        if (i == 0) first = e; else pt_release_event(e);
+    }
+    return first;
+}
+
 extern "C" pt_event pt_multi_launch_pathtracer(pt_multi m, const pt_camera *cam, const pt_render_params *params) {
     if (m->n == 1) return pt_launch_pathtracer(m->ctx[0], cam, params);
     const size_t npix = (size_t)params->width * params->height;
@@ -862,6 +962,7 @@ extern "C" int pt_multi_get_counters(pt_multi m, pt_counters *out) {
         if (rc) return rc;
         out->samples += c.samples; out->rays += c.rays; out->shadow_rays += c.shadow_rays; out->tri_tests += c.tri_tests;
         out->cells_visited += c.cells_visited; out->prim_tests += c.prim_tests; out->tri_tests_executed += c.tri_tests_executed;
+        out->vpl_evals += c.vpl_evals;
     }
     return 0;
 }

@@ -29,15 +29,29 @@ def test_library_exports_every_declared_symbol():
         assert n in _lib.PTCUDA_SYMBOLS, "ctypes table misses %s" % n
     for n in declared_functions("pthost.h"):
         assert hasattr(host, n), "libpthost.so does not export %s" % n
-    assert cuda.pt_abi_version() == 1
+    assert cuda.pt_abi_version() == 2
 
 
-def test_struct_layouts_match_header():
-    assert C.sizeof(_lib.pt_scene) == 36 + 36 + 8 + 4 + 80 + 4 + 4 or C.sizeof(_lib.pt_scene) % 8 == 0
-    assert C.sizeof(_lib.pt_camera) == 64
-    assert C.sizeof(_lib.pt_grid) == 68
-    assert C.sizeof(_lib.pt_render_params) == 4 * 6 + 16 + 4 * 9
-    assert C.sizeof(_lib.pt_counters) == 56
+def test_struct_layouts_match_header(tmp_path):
+    """sizeof / offsetof of every ABI struct, as gcc sees include/ptcuda.h, against the ctypes mirrors."""
+    import subprocess
+    structs = {"pt_scene": _lib.pt_scene, "pt_camera": _lib.pt_camera, "pt_grid": _lib.pt_grid,
+               "pt_render_params": _lib.pt_render_params, "pt_counters": _lib.pt_counters}
+    lines = []
+    for name, cls in structs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (name, name))
+        for f, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (name, f, name, f))
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "ptcuda.h"\nint main(void){%s return 0;}\n' % "".join(lines))
+    exe = str(tmp_path / "layout")
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, str(src)])
+    got = dict(l.split() for l in subprocess.check_output([exe], text=True).splitlines())
+    for name, cls in structs.items():
+        assert int(got[name]) == C.sizeof(cls), name
+        for f, _ in cls._fields_:
+            assert int(got["%s.%s" % (name, f)]) == getattr(cls, f).offset, (name, f)
+    assert C.sizeof(_lib.pt_camera) == 64 and C.sizeof(_lib.pt_grid) == 68
 
 
 @pytest.mark.skipif(_lib.cuda_lib().pt_device_count() > 0, reason="only meaningful without a GPU")
