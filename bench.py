@@ -52,6 +52,11 @@ WORKLOADS = {
                             desc="CLSuperPathTracer_lmem scene, 512x512, 64 spp"),
     "grid_512x512x64": dict(variant="grid", scene="grid", mesh=None, W=512, H=512, spp=64,
                             desc="CLSuperPathTracer_trianglegrid default scene (96 triangles, 8x5x6 grid), 512x512, 64 spp"),
+    "bidir_512x512x64": dict(variant="bidir", scene="bidir", mesh=None, W=512, H=512, spp=64,
+                             desc="CLSuperBidirectionalPathTracer default scene (512 VPLs per light, 2 lights, 96 triangles), 512x512, "
+                                  "64 spp; a step = light-tracing pass + path-tracing pass"),
+    "bidir_1920x1080x64": dict(variant="bidir", scene="bidir", mesh=None, W=1920, H=1080, spp=64,
+                               desc="CLSuperBidirectionalPathTracer default scene, 1920x1080, 64 spp; a step = light + path pass"),
     "torus_1920x1080x1024": dict(variant="base", scene="base", mesh="torus", W=1920, H=1080, spp=1024,
                                  desc="CLSuperPathTracer with torus.txt (32 triangles), DoF, 1920x1080, 1024 spp"),
     "base_1920x1080x1024": dict(variant="base", scene="base", mesh=None, W=1920, H=1080, spp=1024,
@@ -183,14 +188,15 @@ def run_port_band(w, d, H, rows):
 
 def run_reference_once(w, d, H):
     """Run the reference's own CPU implementation of this workload once; returns (kernel_ms, kind, cores)."""
-    ref_bin = os.path.join(ROOT, "oracle", "_ref", "bin", w["variant"], "CLSuperPathTracer")
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "bin", w["variant"], ref_exe_name(w))
     env = dict(os.environ, PT_SEEDS=",".join(str(s) for s in SEEDS))
     cores = os.cpu_count() or 1
     env.setdefault("OMP_NUM_THREADS", str(cores))
     if os.path.exists(ref_bin) and w["spp"] == 64:
         out = subprocess.run([ref_bin, str(w["W"]), str(H)], cwd=d, env=env, capture_output=True, text=True, check=True).stdout
         ms = 0.0
-        for pat in (r"rendering : .* in ([0-9.eE+-]+)ms", r"reduce img samples : .* in ([0-9.eE+-]+)ms"):
+        for pat in (r"rendering : .* in ([0-9.eE+-]+)ms", r"reduce img samples : .* in ([0-9.eE+-]+)ms",
+                    r"virtual light sampling : .* in ([0-9.eE+-]+)ms"):
             m = re.search(pat, out)
             if m:
                 ms += float(m.group(1))
@@ -203,6 +209,10 @@ def run_reference_once(w, d, H):
                          capture_output=True, text=True, check=True).stdout
     stats = json.loads(out[out.index("ORACLE_STATS") + len("ORACLE_STATS"):])
     return stats["ms"], "port", cores
+
+
+def ref_exe_name(w):
+    return "CLSuperBidirectionalPathTracer" if w["variant"] == "bidir" else "CLSuperPathTracer"
 
 
 def is_heavy(w):
@@ -233,7 +243,7 @@ def cpu_reference_measure(w, d, H):
 def reference_opencl_on_gpu(w, d, H, rays):
     """The unmodified reference run by NVIDIA's OpenCL runtime on this GPU (oracle/_ref/ocl, if built and the
     ICD is usable): the "same kernel, same box" baseline.  Returns a dict or None."""
-    exe = os.path.join(ROOT, "oracle", "_ref", "ocl", w["variant"], "CLSuperPathTracer")
+    exe = os.path.join(ROOT, "oracle", "_ref", "ocl", w["variant"], ref_exe_name(w))
     if not os.path.exists(exe) or is_heavy(w):
         return None
     env = dict(os.environ, OCL_ICD_FILENAMES="libnvidia-opencl.so.1", PT_SEEDS=",".join(str(s) for s in SEEDS))
@@ -243,7 +253,7 @@ def reference_opencl_on_gpu(w, d, H, rays):
             p = subprocess.run([exe, str(w["W"]), str(H)], cwd=d, env=env, capture_output=True, text=True, timeout=300)
             if p.returncode != 0:
                 return None
-            ms = sum(float(x) for x in re.findall(r"(?:rendering|reduce img samples) : .*? in ([0-9.eE+-]+)ms", p.stdout))
+            ms = sum(float(x) for x in re.findall(r"(?:rendering|reduce img samples|virtual light sampling) : .*? in ([0-9.eE+-]+)ms", p.stdout))
             best = ms if best is None else min(best, ms)
     except Exception:
         return None
@@ -339,7 +349,11 @@ def bench_ours(args, w, wname):
     accum = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda") if world > 1 else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
+    bidir = w["variant"] == "bidir"
+
     def step():
+        if bidir:                                # the light pass is part of the path (every rank traces the same VPLs)
+            r.light_tracer(SEEDS, 512, wait=False)
         if world > 1:
             accum.zero_()
             r.render_device(w["variant"], W, H, SEEDS, rgba.data_ptr(), accum.data_ptr(), **kw)
@@ -425,6 +439,14 @@ def bench_ours(args, w, wname):
         # executed work of rank 0's share: analytic part of every ray + the triangle tests actually run
         F_analytic = F - 58 * scene.ntriangles
         flops_exec = F_analytic * counters["rays"] + 58.0 * counters["tri_tests_executed"] + 30.0 * counters["cells_visited"]
+        vpl_info = None
+        if bidir:
+            vp = r.read_vpls()
+            nact = int((vp[:, 3] != 0).sum())                  # entries the gather visits (NaN counts, as in the reference)
+            hit_samples = counters["shadow_rays"] // max(1, scene.lights.shape[0])
+            flops_exec += 22.0 * hit_samples * nact            # ~22 flop per (hit sample, non-zero VPL)
+            vpl_info = {"buffer": int(vp.shape[0]), "non_zero": nact, "reference_loop_iterations": counters["vpl_evals"],
+                        "executed_evaluations": hit_samples * nact}
         achieved = flops_exec / (kernel_ms * 1e-3) / 1e12
         nominal = (F if w["variant"] != "grid" else F_analytic) * rays_per_gpu / (kernel_ms * 1e-3) / 1e12
         grid_bytes = 8.0 * counters["cells_visited"] + 48.0 * counters["tri_tests_executed"] if w["variant"] == "grid" else 0.0
@@ -442,7 +464,7 @@ def bench_ours(args, w, wname):
             "msamples_per_s": samples / 1e3 / ms_per_step, "rays_per_step": rays, "samples_per_step": samples,
             "e2e": {"value": rays / 1e3 / e2e_ms, "unit": "Mrays/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "api": "pt_render_host (scene upload + launch + blocking RGBA8 read)"},
-            "gpu_launches": args.steps * (1 if world == 1 else 2),
+            "gpu_launches": args.steps * ((1 if world == 1 else 2) + (2 if bidir else 0)),
             "clocks": clocks,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
                          "traffic": None, "flops_per_ray": F, "nominal_brute_force_tflops": nominal,
@@ -453,6 +475,8 @@ def bench_ours(args, w, wname):
                          "hbm_achieved_gbs": out_bytes / (kernel_ms * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak,
                          "hbm_peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s"},
         }
+        if vpl_info:
+            line["vpl"] = vpl_info
         try:
             ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_reference_numbers.json"))).get(wname)
             if ncu and world == 1:

@@ -209,13 +209,16 @@ class Renderer:
         return raw.reshape(ncells, 128)
 
     # ---- bidirectional variant (CLSuperBidirectionalPathTracer): virtual point lights ----
-    def light_tracer(self, seeds, n_vlp=512, arith="fma"):
+    def light_tracer(self, seeds, n_vlp=512, arith="fma", wait=True):
         """Kernel lightTracer (CLSuperBidirectionalPathTracer.c:143-184): fills the context's VPL buffer, which the next
-        variant="bidir" render gathers.  Returns the device time in ms."""
+        variant="bidir" render gathers.  Returns the device time in ms (wait=False: only enqueues, returns None)."""
         s = (C.c_uint32 * 4)(*[int(v) & 0xFFFFFFFF for v in seeds])
         evt = self._l.pt_launch_lighttracer(self.ctx, int(n_vlp), s, PT_ARITH[arith])
         if not evt:
             raise PtError("pt_launch_lighttracer failed: %s" % self._l.pt_last_error().decode())
+        if not wait:
+            self._l.pt_release_event(evt)
+            return None
         _check(self._l.pt_wait(evt), "pt_wait")
         ms = self._l.pt_runtime_ms(evt)
         self._l.pt_release_event(evt)
@@ -290,6 +293,11 @@ class Renderer:
                                       t.ctypes.data_as(fp), m.ctypes.data_as(C.POINTER(C.c_int32)), nrm.ctypes.data_as(fp)),
                "pt_probe_trace")
         return m, t, nrm
+
+    def selftest_fastmath(self, npairs, seed=1):
+        out = (C.c_uint64 * 3)()
+        _check(self._l.pt_selftest_fastmath(self.ctx, int(npairs), int(seed), out), "pt_selftest_fastmath")
+        return {"div_mismatches": int(out[0]), "sqrt_mismatches": int(out[1]), "pairs_tested": int(out[2])}
 
     def probe_rng(self, seeds, gid, nsteps):
         s = (C.c_uint32 * 4)(*[int(v) for v in seeds])

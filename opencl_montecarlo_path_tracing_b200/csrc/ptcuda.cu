@@ -554,7 +554,7 @@ extern "C" pt_event pt_launch_pathtracer(pt_ctx c, const pt_camera *cam, const p
 
 // ------------------------------------------------------------------------------- bidirectional: VPLs
 static int ensure_vpls(pt_ctx c, int n) {
-    if (!c->d_vpl_count) PT_CUDA(cudaMalloc(&c->d_vpl_count, sizeof(int)), "alloc VPL count");
+    if (!c->d_vpl_count) PT_CUDA(cudaMalloc(&c->d_vpl_count, 2 * sizeof(int)), "alloc VPL count");
     const size_t need = n > 0 ? (size_t)n : 1;
     if (c->vpls_cap >= need) return 0;
     cudaFree(c->d_vpls); cudaFree(c->d_vpl_active);
@@ -760,6 +760,21 @@ extern "C" int pt_probe_trace(pt_ctx c, int variant, int arith, int n, const flo
     cudaMemcpyAsync(n_out, d_n, n * 12, cudaMemcpyDeviceToHost, c->stream);
     PT_CUDA(cudaStreamSynchronize(c->stream), "sync probe");
     cudaFree(d_o); cudaFree(d_d); cudaFree(d_t); cudaFree(d_n); cudaFree(d_m);
+    return 0;
+}
+
+extern "C" int pt_selftest_fastmath(pt_ctx c, uint64_t npairs, uint32_t seed, uint64_t out[3]) {
+    PT_CUDA(cudaSetDevice(c->device), "select device");
+    unsigned long long *d;
+    PT_CUDA(cudaMalloc(&d, 3 * sizeof(unsigned long long)), "alloc");
+    cudaMemsetAsync(d, 0, 3 * sizeof(unsigned long long), c->stream);
+    pt::k_selftest_fastmath<<<c->sm_count * 8, 256, 0, c->stream>>>((unsigned long long)npairs, seed, d);
+    PT_CUDA(cudaGetLastError(), "selftest");
+    unsigned long long h[3];
+    cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
+    PT_CUDA(cudaStreamSynchronize(c->stream), "sync selftest");
+    cudaFree(d);
+    out[0] = h[0]; out[1] = h[1]; out[2] = h[2];
     return 0;
 }
 

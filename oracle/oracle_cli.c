@@ -1,7 +1,7 @@
 /*
  * oracle_cli.c — command-line front end of the CPU oracle (TEST INFRASTRUCTURE ONLY).
  *
- *   oracle_cli <base|lmem|nodof|grid> [img_width] [img_height] [CELL_SIZE_MODIFIER]
+ *   oracle_cli <base|lmem|nodof|grid|bidir> [img_width] [img_height] [CELL_SIZE_MODIFIER | N_VLP_per_light]
  *
  * Reads spheres.txt / squares.txt (nodof: planes.txt, falling back to squares.txt) /
  * triangles.txt / lights.txt from the current directory like the reference hosts do
@@ -24,14 +24,14 @@ static double now_ms(void) {
 
 int main(int argc, char **argv) {
     if (argc < 2) {
-        fprintf(stderr, "usage: %s <base|lmem|nodof|grid> [w] [h] [cell_size_modifier]\n", argv[0]);
+        fprintf(stderr, "usage: %s <base|lmem|nodof|grid|bidir> [w] [h] [cell_size_modifier | n_vlp]\n", argv[0]);
         return 2;
     }
     oracle_job J;
     memset(&J, 0, sizeof(J));
-    const char *names[4] = {"base", "lmem", "nodof", "grid"};
+    const char *names[5] = {"base", "lmem", "nodof", "grid", "bidir"};
     J.variant = -1;
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 5; ++i)
         if (!strcmp(argv[1], names[i])) J.variant = i;
     if (J.variant < 0) { fprintf(stderr, "unknown variant %s\n", argv[1]); return 2; }
     J.width = argc > 2 ? atoi(argv[2]) : 512;
@@ -78,6 +78,14 @@ int main(int argc, char **argv) {
     uint8_t *img = (uint8_t *)malloc((size_t)J.width * J.height * 4);
     oracle_counters c;
     double t0 = now_ms();
+    float *vpls = NULL;
+    if (J.variant == ORACLE_BIDIR) {     /* light pass first, same seeds (CLSuperBidirectionalPathTracer.c:370-375); timed */
+        int n_vlp = argc > 4 ? atoi(argv[4]) : 512;
+        vpls = (float *)malloc(sizeof(float) * 4 * (size_t)(n_vlp > 0 ? n_vlp : 1) * (J.nlights > 0 ? J.nlights : 1));
+        if (oracle_light_tracer(&J, n_vlp, vpls, NULL, NULL)) { fprintf(stderr, "oracle_light_tracer: bad job\n"); return 1; }
+        J.vpls = vpls;
+        J.nvpl = n_vlp * J.nlights;
+    }
     if (oracle_render(&J, img, NULL, NULL, &c)) { fprintf(stderr, "oracle_render: bad job\n"); return 1; }
     double ms = now_ms() - t0;
     const char *out = getenv("PT_OUT") ? getenv("PT_OUT") : "result.ppm";
@@ -88,6 +96,6 @@ int main(int argc, char **argv) {
            names[J.variant], J.width, J.height, J.spp, ms, (unsigned long long)c.samples, (unsigned long long)c.rays,
            (unsigned long long)c.shadow_rays, (unsigned long long)c.tri_tests, (unsigned long long)c.cells_visited,
            (unsigned long long)c.prim_tests, oracle_contract_mode());
-    free(img); free(tris); free(cell_start); free(cell_refs);
+    free(img); free(tris); free(cell_start); free(cell_refs); free(vpls);
     return 0;
 }

@@ -149,6 +149,16 @@ def test_other_light_counts(renderer, scene_dirs, oracle_fma, nlights):
     renderer.set_scene(pt.load_scene_dir(scene_dirs["bidir"], "bidir"))
 
 
+def test_fast_math_is_exact(renderer):
+    """The branch-free division / square root of the gather against the library's IEEE functions."""
+    tested = 0
+    for seed in (1, 2, 3, 4):
+        out = renderer.selftest_fastmath(1 << 30, seed)
+        assert out["div_mismatches"] == 0 and out["sqrt_mismatches"] == 0, out
+        tested += out["pairs_tested"]
+    assert tested > 3 << 30
+
+
 def test_errors(scene_dirs):
     with pt.Renderer(0) as r:
         r.set_scene(pt.load_scene_dir(scene_dirs["bidir"], "bidir"))

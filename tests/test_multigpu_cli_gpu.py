@@ -15,12 +15,12 @@ BIN = os.path.join(ROOT, "opencl_montecarlo_path_tracing_b200", "bin")
 
 
 @pytest.mark.parametrize("variant,dirname", [("nodof", "CLSuperPathTracer_lmem_NoDoF"), ("grid", "CLSuperPathTracer_trianglegrid"),
-                                             ("base", "CLSuperPathTracer")])
+                                             ("base", "CLSuperPathTracer"), ("bidir", "CLSuperBidirectionalPathTracer")])
 def test_pt_gpus_is_bit_identical(scene_dirs, variant, dirname):
     ngpu = _lib.cuda_lib().pt_device_count()
     if ngpu < 2:
         pytest.skip("needs at least 2 GPUs")
-    exe = os.path.join(BIN, dirname, "CLSuperPathTracer")
+    exe = os.path.join(BIN, dirname, "CLSuperBidirectionalPathTracer" if variant == "bidir" else "CLSuperPathTracer")
     d = scene_dirs[variant]
     imgs = {}
     for n in (1, min(ngpu, 8)):

@@ -19,7 +19,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, scene_dir, out_path):
+def _worker(rank, world, port, scene_dir, out_path, variant):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -29,7 +29,9 @@ def _worker(rank, world, port, scene_dir, out_path):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     o = OracleLib(0)
-    sc = o.load_scene_dir(scene_dir, "lmem")
+    sc = o.load_scene_dir(scene_dir, variant)
+    # bidir: every rank traces the light pass itself (same seeds -> the same VPL buffer on every rank, no exchange)
+    extra = {"vpls": o.light_tracer((1, 2, 3, 4), sc, 512)} if variant == "bidir" else {}
     W, H, stripe = 128, 64, 8
     acc = np.zeros((H, W, 4), np.float32)
     rows = sharding.stripe_rows(H, stripe, rank, world)
@@ -37,7 +39,7 @@ def _worker(rank, world, port, scene_dir, out_path):
     runs = np.split(rows, np.where(np.diff(rows) != 1)[0] + 1)
     for run in runs:
         if len(run):
-            part = o.render("lmem", W, H, (1, 2, 3, 4), sc, rows=(int(run[0]), int(run[-1]) + 1), want_rng=False, nthreads=2)
+            part = o.render(variant, W, H, (1, 2, 3, 4), sc, rows=(int(run[0]), int(run[-1]) + 1), want_rng=False, nthreads=2, **extra)
             acc[run[0]:run[-1] + 1] = part["accum"][run[0]:run[-1] + 1]
     t = torch.from_numpy(acc)
     dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
@@ -47,11 +49,12 @@ def _worker(rank, world, port, scene_dir, out_path):
     dist.destroy_process_group()
 
 
-def test_two_rank_stripes_reduce_to_the_full_frame(scene_dirs, tmp_path, oracle_sep):
+@pytest.mark.parametrize("variant", ["lmem", "bidir"])
+def test_two_rank_stripes_reduce_to_the_full_frame(scene_dirs, tmp_path, oracle_sep, variant):
     import torch.multiprocessing as mp
     out = str(tmp_path / "acc.npy")
     port = _free_port()
-    mp.spawn(_worker, args=(2, port, scene_dirs["lmem"], out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, scene_dirs[variant], out, variant), nprocs=2, join=True)
     got = np.load(out)
-    full = oracle_sep.render("lmem", 128, 64, (1, 2, 3, 4), oracle_sep.load_scene_dir(scene_dirs["lmem"], "lmem"), want_rng=False)
+    full = oracle_sep.render(variant, 128, 64, (1, 2, 3, 4), oracle_sep.load_scene_dir(scene_dirs[variant], variant), want_rng=False)
     assert np.array_equal(got.view(np.uint32), full["accum"].view(np.uint32))
