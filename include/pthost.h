@@ -12,9 +12,12 @@
  *   grid sizing             ..._trianglegrid/CLSuperPathTracer.c:476-483   pth_grid_dims
  *   save_pam                pamalign.h:212-238                        pth_save_pam
  *   seeds                   CLSuperPathTracer.c:209                   pth_seeds
+ *   load_pam (+ imgInfo)    pamalign.h:13-21, 52-131, 166-210         pth_load_pam / pth_image
+ * Formats the reference lacks: pth_save_ppm (real P6), pth_save_png, pth_import_obj.
  */
 #ifndef PTHOST_H
 #define PTHOST_H
+#include <stddef.h>
 #include <stdint.h>
 #include "ptcuda.h"
 #ifdef __cplusplus
@@ -31,6 +34,22 @@ int pth_parse_lights(const char *path, float lights[5][4], int print_lights);
 void pth_camera(pt_camera *cam);
 void pth_grid_dims(const float box_min[4], const float box_max[4], int ntriangles, float cell_size_modifier, pt_grid *grid);
 int pth_save_pam(const char *path, int width, int height, const void *rgba8);
+/* imgInfo of pamalign.h:13-21 */
+typedef struct pth_image {
+    uint32_t width, height, channels, maxval;
+    uint32_t depth;      /* bits per value: 8 or 16 */
+    size_t data_size;
+    void *data;          /* malloc'ed; 3-channel images are padded to 4 values per pixel, 16-bit values host-endian */
+} pth_image;
+/* load_pam (pamalign.h:166-210): returns 0 on success, 1 on any error (message on stderr, like the reference). */
+int pth_load_pam(const char *path, pth_image *img);
+void pth_free_image(pth_image *img);
+/* Binary P6 PPM (alpha dropped) / 8-bit RGBA PNG of an RGBA8 frame such as pt_map_render returns. 0 = ok. */
+int pth_save_ppm(const char *path, int width, int height, const void *rgba8);
+int pth_save_png(const char *path, int width, int height, const void *rgba8);
+/* Wavefront OBJ -> triangles.txt (the text layout parseTrianglesFromFile reads); coordinates scale*c + translate.
+ * Returns the triangle count, -1 on error. */
+long pth_import_obj(const char *obj_path, const char *triangles_txt_path, float scale, const float translate[3]);
 /* PT_SEEDS=a,b,c,d if set, else the reference's wall-clock recipe masked to 27 bits */
 void pth_seeds(uint32_t seeds[4]);
 

@@ -85,6 +85,13 @@ class pt_counters(C.Structure):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
+class pth_image(C.Structure):
+    _fields_ = [
+        ("width", C.c_uint32), ("height", C.c_uint32), ("channels", C.c_uint32), ("maxval", C.c_uint32),
+        ("depth", C.c_uint32), ("data_size", C.c_size_t), ("data", C.c_void_p),
+    ]
+
+
 _VP, _I, _D = C.c_void_p, C.c_int, C.c_double
 _FP, _U32P, _I32P = C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_int32)
 
@@ -142,6 +149,11 @@ PTHOST_SYMBOLS = {
     "pth_grid_dims": (None, [_FP, _FP, _I, C.c_float, C.POINTER(pt_grid)]),
     "pth_save_pam": (_I, [C.c_char_p, _I, _I, _VP]),
     "pth_seeds": (None, [_U32P]),
+    "pth_load_pam": (_I, [C.c_char_p, C.POINTER(pth_image)]),
+    "pth_free_image": (None, [C.POINTER(pth_image)]),
+    "pth_save_ppm": (_I, [C.c_char_p, _I, _I, _VP]),
+    "pth_save_png": (_I, [C.c_char_p, _I, _I, _VP]),
+    "pth_import_obj": (C.c_long, [C.c_char_p, C.c_char_p, C.c_float, _FP]),
     "pth_cli_main": (_I, [_I, _I, C.POINTER(C.c_char_p)]),
 }
 

@@ -115,6 +115,42 @@ def save_pam(path, image):
         raise PtError("error writing %s" % path)
 
 
+def load_pam(path):
+    """pamalign.h load_pam: -> (array (H, W, C') uint8/uint16, maxval); 3-channel files come back padded to 4."""
+    img = _lib.pth_image()
+    if _lib.host_lib().pth_load_pam(path.encode(), C.byref(img)):
+        raise PtError("error reading %s" % path)
+    try:
+        stride = img.channels + (1 if img.channels == 3 else 0)
+        dt = np.uint8 if img.depth == 8 else np.uint16
+        n = img.width * img.height * stride
+        arr = np.ctypeslib.as_array(C.cast(img.data, C.POINTER(C.c_uint8 if img.depth == 8 else C.c_uint16)), shape=(max(n, 1),))[:n]
+        return arr.astype(dt).reshape(img.height, img.width, stride).copy(), int(img.maxval)
+    finally:
+        _lib.host_lib().pth_free_image(C.byref(img))
+
+
+def save_ppm(path, image):
+    img = np.ascontiguousarray(image, dtype=np.uint8)
+    if _lib.host_lib().pth_save_ppm(path.encode(), img.shape[1], img.shape[0], img.ctypes.data_as(C.c_void_p)):
+        raise PtError("error writing %s" % path)
+
+
+def save_png(path, image):
+    img = np.ascontiguousarray(image, dtype=np.uint8)
+    if _lib.host_lib().pth_save_png(path.encode(), img.shape[1], img.shape[0], img.ctypes.data_as(C.c_void_p)):
+        raise PtError("error writing %s" % path)
+
+
+def import_obj(obj_path, triangles_txt_path, scale=1.0, translate=(0.0, 0.0, 0.0)):
+    """Wavefront OBJ -> triangles.txt; returns the number of triangles written."""
+    t = (C.c_float * 3)(*[float(x) for x in translate])
+    n = _lib.host_lib().pth_import_obj(obj_path.encode(), triangles_txt_path.encode(), C.c_float(scale), t)
+    if n < 0:
+        raise PtError("error importing %s" % obj_path)
+    return int(n)
+
+
 @dataclass
 class RenderResult:
     image: np.ndarray                 # (H, W, 4) uint8

@@ -19,6 +19,7 @@
  *   PT_DEVICE / OCL_DEVICE   device index
  *   PT_GPUS=n          render on GPUs 0..n-1 of this box (row stripes + one NCCL reduce of the accumulation buffer)
  *   PT_NO_WARMUP=1     skip the untimed one-row warm-up launch
+ *   PT_EXTRA_OUTPUT=png,ppm   additionally write result.png (RGBA PNG) and/or result_p6.ppm (binary P6) next to result.ppm
  *   PT_STATS=1         append Mrays/s, samples/s and work counters after the reference's own lines
  */
 #define _GNU_SOURCE
@@ -162,6 +163,9 @@ int pth_cli_main(int variant, int argc, char **argv) {
         exit(1);
     } else
         printf("\nSuccessfully created render image %s in the current directory\n\n", image_name);
+    const char *extra = getenv("PT_EXTRA_OUTPUT");
+    if (extra && strstr(extra, "png") && pth_save_png("result.png", img_width, img_height, pixels)) pt_check(1, "write result.png");
+    if (extra && strstr(extra, "ppm") && pth_save_ppm("result_p6.ppm", img_width, img_height, pixels)) pt_check(1, "write result_p6.ppm");
 
     double render_ms = pt_runtime_ms(render_evt), read_ms = pt_runtime_ms(read_evt), light_ms = 0.0;
     if (bidir) {

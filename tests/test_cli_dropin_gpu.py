@@ -61,3 +61,24 @@ def test_cli_wall_clock_seeds_and_error_convention(scene_dirs, tmp_path):
     # a missing scene file is reported ocl_check-style ("<what> - error <n>", exit status 1) instead of crashing
     q = subprocess.run([exe, "64", "64"], cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=120)
     assert q.returncode == 1 and " - error " in q.stderr
+
+
+def test_cli_extra_outputs(scene_dirs):
+    """PT_EXTRA_OUTPUT=png,ppm: the same frame as result.ppm (PAM) in PNG and binary P6."""
+    import zlib
+    import opencl_montecarlo_path_tracing_b200 as pt
+    exe = os.path.join(BIN, DIRS["lmem"], "CLSuperPathTracer")
+    d = scene_dirs["lmem"]
+    env = dict(os.environ, PT_SEEDS="1,2,3,4", PT_EXTRA_OUTPUT="png,ppm")
+    p = subprocess.run([exe, "96", "64"], cwd=d, env=env, capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr
+    pam, _ = pt.load_pam(os.path.join(d, "result.ppm"))
+    assert pam.shape == (64, 96, 4)
+    raw = open(os.path.join(d, "result_p6.ppm"), "rb").read()
+    hdr = b"P6\n96 64\n255\n"
+    assert raw.startswith(hdr) and np.array_equal(np.frombuffer(raw[len(hdr):], np.uint8).reshape(64, 96, 3), pam[..., :3])
+    png = open(os.path.join(d, "result.png"), "rb").read()
+    k = png.index(b"IDAT")
+    n = int.from_bytes(png[k - 4:k], "big")
+    rows = np.frombuffer(zlib.decompress(png[k + 4:k + 4 + n]), np.uint8).reshape(64, 96 * 4 + 1)
+    assert np.array_equal(rows[:, 1:].reshape(64, 96, 4), pam)
