@@ -261,6 +261,23 @@ def reference_opencl_on_gpu(w, d, H, rays):
             "what": "unmodified reference .c + .ocl, NVIDIA OpenCL ICD on the same B200, OpenCL event time, best of 3"}
 
 
+def simple_cpu_tracer_baseline():
+    """SimpleCPUTracer (the reference's single-threaded CPU tracer; its own hard-wired scene and rand(), so a reported
+    baseline only, never an oracle), built from the reference source into oracle/_ref by `make -C oracle ref`."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "bin", "simplecpu", "simpleCPUtracer")
+    if not os.path.exists(exe):
+        return None
+    try:
+        with tempfile.TemporaryDirectory() as t:
+            out = subprocess.run([exe, "256", "256"], cwd=t, capture_output=True, text=True, timeout=300, check=True).stdout
+        ms = float(re.search(r"rendering \(host\) : .* in ([0-9.eE+-]+)ms", out).group(1))
+    except Exception:
+        return None
+    samples = 256 * 256 * 64
+    return {"value": samples / 1e3 / ms, "unit": "Msamples/s", "cores": 1, "ms": ms, "kind": "reference",
+            "sample": "SimpleCPUTracer, its built-in scene, 256x256x64 (serial rand(): one thread by construction)"}
+
+
 def reference_rays(w, d, H):
     """Ray count of the frame (same seeds) from the oracle's counters, to turn reference times into Mrays/s."""
     from oracle import pyoracle
@@ -497,6 +514,10 @@ def bench_ours(args, w, wname):
                                         "ms": m["ms"], "sample": m["sample"]}
                 if ocl:
                     line["reference_opencl_same_gpu"] = ocl
+                if wname == DEFAULT_WORKLOAD:
+                    sct = simple_cpu_tracer_baseline()
+                    if sct:
+                        line["simple_cpu_tracer"] = sct
             except Exception as exc:  # pragma: no cover - reporting only
                 line["cpu_baseline"] = {"error": str(exc)}
         sys.stdout.flush()

@@ -119,6 +119,7 @@ int pt_launch_persistent(pt_ctx ctx, const pt_render_params *p, const pt::Launch
 int pt_launch_wavefront(pt_ctx ctx, const pt_render_params *p, const pt::LaunchArgs &args);
 int pt_launch_grid_tma(pt_ctx ctx, const pt_render_params *p, const pt::LaunchArgs &args);
 int pt_grid_build_device(pt_ctx ctx, const pt_grid *g);
+int pt_launch_stream_grid(pt_ctx ctx, const pt_render_params *p, const pt::LaunchArgs &args);
 int pt_launch_bidir(pt_ctx ctx, const pt_render_params *p, const pt::LaunchArgs &args);
 int pt_launch_light_tracer_kernels(pt_ctx ctx, int arith, const pt::LaunchArgs &args, int n, float4 *vpl, uint4 *rng_out,
                                    float4 *active, int *count);

@@ -20,6 +20,7 @@
 #include "pt_gridbuild.cuh"
 #include "pt_gridtma.cuh"
 #include "pt_bidir.cuh"
+#include "pt_gridstream.cuh"
 
 // ------------------------------------------------------------------------------------ errors
 static int g_error_mode = PT_ERRORS_EXIT;
@@ -519,6 +520,9 @@ static int dispatch(pt_ctx c, const pt_render_params *pin, const pt::LaunchArgs 
     switch (p->kernel) {
         case PT_KERNEL_MEGA: return pt_launch_mega(c, p, A);
         case PT_KERNEL_PERSISTENT: return pt_launch_persistent(c, p, A);
+        case PT_KERNEL_GRID_STREAM:
+            if (p->variant != PT_VARIANT_GRID) return pt_fail(1, "PT_KERNEL_GRID_STREAM applies to the trianglegrid variant only");
+            return pt_launch_stream_grid(c, p, A);
         case PT_KERNEL_WAVEFRONT: return pt_launch_wavefront(c, p, A);
         case PT_KERNEL_GRID_TMA: return pt_launch_grid_tma(c, p, A);
     }

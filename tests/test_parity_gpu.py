@@ -149,7 +149,8 @@ def _soup_scene(n, seed, box):
 
 
 @pytest.mark.parametrize("n,box,kernel", [(30000, 24.0, "mega"), (30000, 24.0, "persistent"), (30000, 24.0, "wavefront"),
-                                          (30000, 24.0, "grid_tma"), (70000, 30.0, "mega")])
+                                          (30000, 24.0, "grid_tma"), (30000, 24.0, "grid_stream"), (70000, 30.0, "mega"),
+                                          (70000, 30.0, "grid_stream")])
 def test_grid_synthetic_soup_bit_exact(renderer, oracle_fma, n, box, kernel):
     """Uniform-grid traversal on a seeded triangle soup (the config-4/5 generator at test size); 70000
     triangles exceed the reference's 16-bit cell ids (wide ids).  The camera sits inside the box."""
@@ -172,8 +173,10 @@ def test_grid_synthetic_soup_bit_exact(renderer, oracle_fma, n, box, kernel):
     assert res.counters["cells_visited"] > 0 and res.counters["tri_tests"] > 0
 
 
-def test_grid_tma_default_scene_and_dense_cells(renderer, scene_dirs, oracle_fma):
-    """TMA-staged warp-per-ray traversal: default grid scene, and CELL_SIZE_MODIFIER 0.02 (one fat cell capped at 62)."""
+@pytest.mark.parametrize("kernel", ["grid_tma", "grid_stream"])
+def test_grid_tma_default_scene_and_dense_cells(renderer, scene_dirs, oracle_fma, kernel):
+    """TMA-staged warp-per-ray traversal and cell-granular regeneration: default grid scene, and CELL_SIZE_MODIFIER 0.02
+    (one fat cell capped at 62)."""
     d = scene_dirs["grid"]
     scene = pt.load_scene_dir(d, "grid")
     renderer.set_scene(scene)
@@ -182,7 +185,7 @@ def test_grid_tma_default_scene_and_dense_cells(renderer, scene_dirs, oracle_fma
     for mod, rows in ((3.0, (112, 144)), (0.02, (120, 136))):
         g = pt.grid_dims(scene, mod)
         renderer.build_grid(g)
-        res = renderer.render("grid", W, H, SEED_SETS[0], rows=rows, kernel="grid_tma", want_accum=True, want_rng=True)
+        res = renderer.render("grid", W, H, SEED_SETS[0], rows=rows, kernel=kernel, want_accum=True, want_rng=True)
         ref = oracle_fma.render("grid", W, H, SEED_SETS[0], osc, rows=rows, modifier=mod, grid=None)
         r0, r1 = rows
         assert np.array_equal(res.image[r0:r1], ref["image"][r0:r1]), mod
@@ -234,7 +237,7 @@ def test_full_size_flavours_agree(renderer, scene_dirs):
     tiling produce bit-identical accumulation buffers (spp reduced to 16; work is identical per sample)."""
     W, H, spp = 1920, 1080, 16
     for variant, flavours in (("base", ("mega", "persistent", "wavefront")), ("nodof", ("mega", "persistent", "wavefront")),
-                              ("grid", ("mega", "persistent", "wavefront", "grid_tma"))):
+                              ("grid", ("mega", "persistent", "wavefront", "grid_tma", "grid_stream"))):
         scene = pt.load_scene_dir(scene_dirs[variant], variant)
         renderer.set_scene(scene)
         if variant == "grid":

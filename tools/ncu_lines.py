@@ -49,6 +49,8 @@ def main():
     rows = list(csv.reader(out.splitlines()))
     hdr = rows[1]
     ie = hdr.index("Instructions Executed")
+    ite = hdr.index("Thread Instructions Executed")
+    ist = hdr.index("Warp Stall Sampling (All Samples)")
     data = [r for r in rows[2:] if len(r) > ie and r[0].startswith("0x")]
     # the csv may list the kernel twice; keep the first pass (addresses strictly increasing)
     first = []
@@ -64,21 +66,27 @@ def main():
         print("warning: %d SASS instructions in cubin vs %d in report" % (len(loc), len(first)))
     n = min(len(loc), len(first))
     per_line = {}
-    per_func_line = {}
-    tot = 0
+    per_thr = {}
+    per_stall = {}
+    tot = tot_thr = tot_stall = 0
     for k in range(n):
         c = int(first[k][ie])
         tot += c
         key = loc[k][:2]
         per_line[key] = per_line.get(key, 0) + c
+        th = int(first[k][ite] or 0); st = int(first[k][ist] or 0)
+        per_thr[key] = per_thr.get(key, 0) + th
+        per_stall[key] = per_stall.get(key, 0) + st
+        tot_thr += th; tot_stall += st
     srcs = {}
-    print("total executed warp instructions: %d" % tot)
+    print("total executed warp instructions: %d   avg active threads %.2f   stall samples %d" % (tot, tot_thr / max(tot, 1), tot_stall))
+    print(" warp-inst%  thr/inst  stall%   file:line")
     for (f, l), c in sorted(per_line.items(), key=lambda kv: -kv[1])[:top]:
         if f not in srcs:
             p = os.path.join(ROOT, "opencl_montecarlo_path_tracing_b200/csrc", f)
             srcs[f] = open(p).read().split("\n") if os.path.exists(p) else []
         text = srcs[f][l - 1].strip()[:100] if 0 < l <= len(srcs[f]) else ""
-        print("%6.2f%%  %-18s %4d  %s" % (100.0 * c / tot, f, l, text))
+        print("%6.2f%%  %5.1f  %6.2f%%  %-18s %4d  %s" % (100.0 * c / tot, per_thr[(f, l)] / max(c, 1), 100.0 * per_stall[(f, l)] / max(tot_stall, 1), f, l, text))
 
 
 if __name__ == "__main__":
