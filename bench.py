@@ -347,7 +347,12 @@ def bench_ours(args, w, wname):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    W, H, spp = w["W"], (w["H"] if args.strong else w["H"] * world), w["spp"]
+    by_samples = args.shard == "samples" and world > 1
+    if by_samples and w["variant"] == "nodof":
+        raise SystemExit("--shard samples is for the per-pixel-stream variants (NoDoF shards by tiles)")
+    W, H, spp = w["W"], (w["H"] if args.strong or by_samples else w["H"] * world), w["spp"]
+    if by_samples and not args.strong:
+        spp *= world                             # weak scaling in the sample dimension
     tmp = tempfile.TemporaryDirectory()
     d = scene_dir_for(w, tmp.name)
     scene = load_workload_scene(w, d)
@@ -359,7 +364,9 @@ def bench_ours(args, w, wname):
     kw = dict(spp=spp, kernel=args.kernel, arith="fma")
     if args.scene_mem:
         kw["scene_mem"] = args.scene_mem
-    if world > 1:
+    if by_samples:
+        kw.update(sample_block=rank, sample_blocks=world)
+    elif world > 1:
         kw.update(interleave=8, rank=rank, nranks=world)
 
     rgba = torch.zeros((H, W), dtype=torch.int32, device="cuda")
@@ -476,7 +483,8 @@ def bench_ours(args, w, wname):
             "config": {"workload": wname, "description": w["desc"], "width": W, "height": H, "spp": spp, "seeds": list(SEEDS),
                        "kernel": args.kernel, "scene_mem": args.scene_mem or "auto",
                        "arith": "fma (bit-exact vs oracle -DPT_CONTRACT=1)", "l2": "flushed between timed steps (256 MiB write)",
-                       "sharding": "8-row stripes round-robin over ranks + one NCCL reduce of the float accumulation buffer"
+                       "sharding": ("sample blocks (spp/N samples of every pixel per rank, re-seeded streams) + one NCCL reduce" if by_samples else
+                                    "8-row stripes round-robin over ranks + one NCCL reduce of the float accumulation buffer")
                        if world > 1 else "single GPU"},
             "msamples_per_s": samples / 1e3 / ms_per_step, "rays_per_step": rays, "samples_per_step": samples,
             "e2e": {"value": rays / 1e3 / e2e_ms, "unit": "Mrays/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
@@ -542,6 +550,9 @@ def main():
     ap.add_argument("--kernel", default="auto", choices=["auto", "mega", "persistent", "wavefront"])
     ap.add_argument("--scene-mem", default=None, choices=["auto", "const", "smem"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", default="tiles", choices=["tiles", "samples"],
+                    help="N>1: tiles = 8-row stripes (bit-identical to 1 GPU); samples = every rank renders a block of each pixel's "
+                         "samples (throughput mode, statistically equivalent; weak scaling grows spp with N)")
     ap.add_argument("--strong", action="store_true", help="N>1: keep the image fixed (strong scaling) instead of growing it with N")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]

@@ -65,6 +65,8 @@ class pt_render_params(C.Structure):
         ("rank", C.c_int32),
         ("nranks", C.c_int32),
         ("no_cull", C.c_int32),
+        ("sample_block", C.c_int32),
+        ("sample_blocks", C.c_int32),
         ("n_vlp", C.c_int32),
     ]
 

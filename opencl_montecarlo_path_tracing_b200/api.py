@@ -161,7 +161,7 @@ class RenderResult:
 
 
 def make_params(variant, width, height, seeds, spp=64, kernel="auto", scene_mem=None, arith="fma", rows=None,
-                want_accum=False, want_rng=False, interleave=0, rank=0, nranks=1, cull=True, n_vlp=0):
+                want_accum=False, want_rng=False, interleave=0, rank=0, nranks=1, cull=True, n_vlp=0, sample_block=0, sample_blocks=0):
     p = pt_render_params()
     p.variant = PT_VARIANT[variant]
     p.width, p.height, p.spp = int(width), int(height), int(spp)
@@ -177,6 +177,7 @@ def make_params(variant, width, height, seeds, spp=64, kernel="auto", scene_mem=
     p.row_interleave, p.rank, p.nranks = int(interleave), int(rank), int(nranks)
     p.no_cull = 0 if cull else 1
     p.n_vlp = int(n_vlp)
+    p.sample_block, p.sample_blocks = int(sample_block), int(sample_blocks)
     return p
 
 

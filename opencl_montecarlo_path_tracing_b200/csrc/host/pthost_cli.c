@@ -18,6 +18,8 @@
  *   PT_MAX_TRIANGLES=n lift the 512 / 65536 MAX_TRIANGLES cap of the reference hosts
  *   PT_DEVICE / OCL_DEVICE   device index
  *   PT_GPUS=n          render on GPUs 0..n-1 of this box (row stripes + one NCCL reduce of the accumulation buffer)
+ *   PT_SHARD=samples   with PT_GPUS=n: shard the SAMPLES of every pixel over the GPUs instead of row stripes (throughput
+ *                      mode: other RNG streams per block, statistically equivalent image, not bit-identical)
  *   PT_NO_WARMUP=1     skip the untimed one-row warm-up launch
  *   PT_EXTRA_OUTPUT=png,ppm   additionally write result.png (RGBA PNG) and/or result_p6.ppm (binary P6) next to result.ppm
  *   PT_STATS=1         append Mrays/s, samples/s and work counters after the reference's own lines
@@ -133,6 +135,7 @@ int pth_cli_main(int variant, int argc, char **argv) {
     rp.scene_mem = env_choice("PT_SCENE_MEM", mems, 3, PT_SCENE_AUTO);
     rp.arith = env_choice("PT_ARITH", ariths, 2, PT_ARITH_FMA);
     rp.no_cull = getenv("PT_NO_CULL") ? atoi(getenv("PT_NO_CULL")) : 0;
+    if (multi && getenv("PT_SHARD") && !strcmp(getenv("PT_SHARD"), "samples")) rp.sample_blocks = ngpus;
 
     pt_event light_evt = NULL;
     if (bidir && !getenv("PT_NO_WARMUP")) {     /* untimed first light pass (lazy module load), also feeds the warm-up render */

@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(128, 5) k_stream_grid(const __grid_constant__ 
     C.ix = C.iy = C.iz = 0;
     C.cell = C.ncell = make_uint2(0u, 0u);
     C.at_end = true;
-    float cx = 13.0f, cy = 13.0f, cz = 13.0f;
+    float cx = P.c0, cy = P.c0, cz = P.c0;
     int s = 0, hit = HIT_NONE;
     uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     bool have = false;      // lane owns a pixel
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(128, 5) k_stream_grid(const __grid_constant__ 
                         } else if (item_to_pixel(P, w, i, j)) {
                             L.px = i; L.py = j;
                             L.rng = rng_seed(P.seeds, (uint32_t)(j * P.W + i));
-                            L.phase = 0; s = 0; cx = cy = cz = 13.0f;
+                            L.phase = 0; s = 0; cx = cy = cz = P.c0;
                             have = true; want = false; done = false;
                         } else {
                             fetch = true;                      // item lies outside the image: draw another
@@ -201,8 +201,8 @@ __global__ void __launch_bounds__(128, 5) k_stream_grid(const __grid_constant__ 
                             cz = A::madd(c.z, P.scale, cz);
                             if (++s == P.spp) {
                                 const size_t pix = (size_t)L.py * P.W + L.px;
-                                P.rgba[pix] = pack_rgba8_rz(cx, cy, cz, 255.0f);
-                                if (P.accum) P.accum[pix] = make_float4(cx, cy, cz, 255.0f);
+                                P.rgba[pix] = pack_rgba8_rz(cx, cy, cz, P.alpha);
+                                if (P.accum) P.accum[pix] = make_float4(cx, cy, cz, P.alpha);
                                 if (P.rng_out) P.rng_out[pix] = make_uint4(L.rng.x0, L.rng.x1, L.rng.c0, L.rng.c1);
                                 have = false; want = true; fetch = true;
                                 start = false;

@@ -13,6 +13,8 @@ struct LaunchArgs {
     uint4 seeds;
     int W, H, spp;
     float scale;            // 224/spp (3.5 at 64 spp)
+    float c0, alpha;        // accumulation start value and alpha written to the float buffer: 13 / 255, or 0 / 0 for the
+                            //   sample blocks b > 0 of a sample-sharded frame (pt_render_params.sample_blocks)
     int row_begin, row_end; // image rows [row_begin, row_end) are eligible
     int nrows;              // number of (virtual) rows this launch walks (see map_row)
     int stripe_h, rank, nranks;  // row interleave (stripe_h == 0: contiguous rows)

@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(128, VARIANT == PT_VARIANT_GRID ? 8 : 6) k_meg
     const int j = map_row(P, vr);
     if (i < P.W && vr < P.nrows && j < P.row_end) {
         Rng rng = rng_seed(P.seeds, (uint32_t)(j * P.W + i));
-        float cx = 13.0f, cy = 13.0f, cz = 13.0f;
+        float cx = P.c0, cy = P.c0, cz = P.c0;
         for (int s = 0; s < P.spp; ++s) {
             V3 o, d;
             camera_ray<FMA>(P.cam, rng, i, j, o, d);
@@ -85,8 +85,8 @@ __global__ void __launch_bounds__(128, VARIANT == PT_VARIANT_GRID ? 8 : 6) k_meg
             cz = Ar<FMA>::madd(c.z, P.scale, cz);
         }
         const size_t pix = (size_t)j * P.W + i;
-        P.rgba[pix] = pack_rgba8_rz(cx, cy, cz, 255.0f);
-        if (P.accum) P.accum[pix] = make_float4(cx, cy, cz, 255.0f);
+        P.rgba[pix] = pack_rgba8_rz(cx, cy, cz, P.alpha);
+        if (P.accum) P.accum[pix] = make_float4(cx, cy, cz, P.alpha);
         if (P.rng_out) P.rng_out[pix] = make_uint4(rng.x0, rng.x1, rng.c0, rng.c1);
     }
     flush_counters(P, cnt, GRID ? 0 : S->ntri_counted, P.ap.nsq + P.ap.nsp);

@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(128, 6) k_sm_pixel(const __grid_constant__ Lau
     Lane L;
     L.phase = 0; L.l = 0; L.mat = 0; L.illum = 0.f; L.lam = 0.f; L.matf = 0.f; L.t = 1e9f;
     L.o = L.d = L.X = L.n = mk3(0.f, 0.f, 0.f);
-    float cx = 13.0f, cy = 13.0f, cz = 13.0f;
+    float cx = P.c0, cy = P.c0, cz = P.c0;
     int s = 0;
     uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     bool have = false;      // lane owns a valid pixel
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(128, 6) k_sm_pixel(const __grid_constant__ Lau
                 } else if (item_to_pixel(P, w, i, j, nitems)) {
                     L.px = i; L.py = j;
                     L.rng = rng_seed(P.seeds, (uint32_t)(j * P.W + i));
-                    L.phase = 0; s = 0; cx = cy = cz = 13.0f;
+                    L.phase = 0; s = 0; cx = cy = cz = P.c0;
                     have = true; want = false;
                 } else if (REGEN) {
                     fetch = true;                      // item lies outside the image: draw another
@@ -173,8 +173,8 @@ __global__ void __launch_bounds__(128, 6) k_sm_pixel(const __grid_constant__ Lau
             cz = Ar<FMA>::madd(c.z, P.scale, cz);
             if (++s == P.spp) {
                 const size_t pix = (size_t)L.py * P.W + L.px;
-                P.rgba[pix] = pack_rgba8_rz(cx, cy, cz, 255.0f);
-                if (P.accum) P.accum[pix] = make_float4(cx, cy, cz, 255.0f);
+                P.rgba[pix] = pack_rgba8_rz(cx, cy, cz, P.alpha);
+                if (P.accum) P.accum[pix] = make_float4(cx, cy, cz, P.alpha);
                 if (P.rng_out) P.rng_out[pix] = make_uint4(L.rng.x0, L.rng.x1, L.rng.c0, L.rng.c1);
                 have = false;
                 want = REGEN;       // fetched at the top of the loop with one warp-aggregated atomicAdd

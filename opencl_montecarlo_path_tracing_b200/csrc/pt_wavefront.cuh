@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) wf_generate(const __grid_constant__ Launc
         rng = rng_seed(P.seeds, (uint32_t)(gj * (8 * P.W) + gi));
     } else if (pass == 0) {
         rng = rng_seed(P.seeds, (uint32_t)(j * P.W + i));
-        B.color[idx] = make_float4(13.0f, 13.0f, 13.0f, 255.0f);
+        B.color[idx] = make_float4(P.c0, P.c0, P.c0, P.alpha);
     } else {
         const uint4 s = B.rng[idx];
         rng.x0 = s.x; rng.x1 = s.y; rng.c0 = s.z; rng.c1 = s.w;
@@ -237,8 +237,8 @@ __global__ void __launch_bounds__(256) wf_resolve(const __grid_constant__ Launch
         x = c.x; y = c.y; z = c.z;
         if (P.rng_out) P.rng_out[pix] = B.rng[idx];
     }
-    P.rgba[pix] = pack_rgba8_rz(x, y, z, 255.0f);
-    if (P.accum) P.accum[pix] = make_float4(x, y, z, 255.0f);
+    P.rgba[pix] = pack_rgba8_rz(x, y, z, NODOF ? 255.0f : P.alpha);
+    if (P.accum) P.accum[pix] = make_float4(x, y, z, NODOF ? 255.0f : P.alpha);
 }
 
 // NoDoF keeps no per-pixel stream; its per-sample final RNG states are written by this helper pass.

@@ -421,9 +421,24 @@ static int validate_params(pt_ctx c, const pt_render_params *p) {
     if (p->spp <= 0) return pt_fail(1, "render: spp must be positive");
     if (p->variant == PT_VARIANT_NODOF && p->spp != 64) return pt_fail(1, "render: the NoDoF variant is defined for 64 samples (8x8 work-items) per pixel");
     if (p->variant == PT_VARIANT_GRID && !c->grid_set) return pt_fail(1, "render: grid variant needs pt_build_grid first");
+    if (p->sample_blocks > 1) {
+        if (p->variant == PT_VARIANT_NODOF) return pt_fail(1, "render: sample sharding is for the per-pixel-stream variants (NoDoF shards by tiles)");
+        if (p->sample_block < 0 || p->sample_block >= p->sample_blocks) return pt_fail(1, "render: sample_block %d outside [0, %d)", p->sample_block, p->sample_blocks);
+        if (p->spp % p->sample_blocks) return pt_fail(1, "render: spp %d is not a multiple of sample_blocks %d", p->spp, p->sample_blocks);
+    }
     if ((long long)p->width * p->height * (p->variant == PT_VARIANT_NODOF ? 64 : 1) > 0x7fffffffLL)
         return pt_fail(1, "render: work-item ids exceed 31 bits (the reference computes them in int)");
     return 0;
+}
+
+// pathtracer.ocl:26-34 on the host (seed derivation of the sample blocks)
+static uint32_t host_randomize_id(uint32_t id) {
+    id = (id ^ 61u) ^ (id >> 16);
+    id *= 9u;
+    id = id ^ (id >> 4);
+    id *= 0x27d4eb2du;
+    id = id ^ (id >> 15);
+    return id;
 }
 
 static int fill_args(pt_ctx c, const pt_camera *cam, const pt_render_params *p, uint32_t *d_rgba, float4 *d_accum, uint4 *d_rng,
@@ -433,6 +448,18 @@ static int fill_args(pt_ctx c, const pt_camera *cam, const pt_render_params *p, 
     A->seeds = make_uint4(p->seeds[0], p->seeds[1], p->seeds[2], p->seeds[3]);
     A->W = p->width; A->H = p->height; A->spp = p->spp;
     A->scale = 224.0f / (float)p->spp;
+    A->c0 = 13.0f; A->alpha = 255.0f;
+    if (p->sample_blocks > 1) {
+        // sample-range sharding ("throughput mode"): block b renders spp/blocks samples per pixel; block 0
+        // continues the reference's own stream, block b > 0 draws from seeds ^ randomizeId(b); only block 0 carries
+        // the bias 13 and alpha 255, so the SUM of the blocks' float buffers is the frame
+        A->spp = p->spp / p->sample_blocks;
+        if (p->sample_block > 0) {
+            const uint32_t h = host_randomize_id((uint32_t)p->sample_block);
+            A->seeds = make_uint4(p->seeds[0] ^ h, p->seeds[1] ^ h, p->seeds[2] ^ h, p->seeds[3] ^ h);
+            A->c0 = 0.0f; A->alpha = 0.0f;
+        }
+    }
     int rb = p->row_begin, re = p->row_end;
     if (re <= 0 || re > p->height) re = p->height;
     if (rb < 0) rb = 0;
@@ -927,7 +954,11 @@ extern "C" pt_event pt_multi_launch_lighttracer(pt_multi m, int n_vlp_per_light,
 }
 
 extern "C" pt_event pt_multi_launch_pathtracer(pt_multi m, const pt_camera *cam, const pt_render_params *params) {
-    if (m->n == 1) return pt_launch_pathtracer(m->ctx[0], cam, params);
+    if (m->n == 1) {
+        pt_render_params p1 = *params;
+        p1.sample_blocks = 0;
+        return pt_launch_pathtracer(m->ctx[0], cam, &p1);
+    }
     const size_t npix = (size_t)params->width * params->height;
     for (int i = 0; i < m->n; ++i) {
         PT_CUDA_NULL(cudaSetDevice(i), "select device");
@@ -944,10 +975,14 @@ extern "C" pt_event pt_multi_launch_pathtracer(pt_multi m, const pt_camera *cam,
     pt_event e = event_new(c0);
     if (!e) return nullptr;
     cudaEventRecord(e->start, c0->stream);
+    // sample_blocks > 1 asks for sample-range sharding instead of tiles: device i renders sample block i of the WHOLE image
+    const bool by_samples = params->sample_blocks > 1;
+    if (by_samples && params->sample_blocks != m->n) { pt_fail(1, "pt_multi: sample_blocks (%d) must equal the number of GPUs (%d)", params->sample_blocks, m->n); return nullptr; }
     for (int i = 0; i < m->n; ++i) {
         PT_CUDA_NULL(cudaSetDevice(i), "select device");
         pt_render_params p = *params;
-        p.row_interleave = 8; p.rank = i; p.nranks = m->n;
+        if (by_samples) { p.sample_block = i; p.row_interleave = 0; p.rank = 0; p.nranks = 1; }
+        else { p.row_interleave = 8; p.rank = i; p.nranks = m->n; }
         PT_CUDA_NULL(cudaMemsetAsync(m->accum[i], 0, npix * 16, m->ctx[i]->stream), "clear accumulation buffer");
         if (pt_render_device(m->ctx[i], cam, &p, m->rgba_scratch[i], m->accum[i])) return nullptr;
     }

@@ -442,6 +442,13 @@ int oracle_render(const oracle_job *J, uint8_t *rgba8, float *accum, uint32_t *r
     oracle_counters total;
     memset(&total, 0, sizeof(total));
     const float scale = 224.0f / (float)J->spp;      /* = 3.5f at the reference's 64 spp */
+    /* sample blocks (extension, oracle.h): fewer samples from a re-seeded stream, bias only in block 0 */
+    const int R = J->sample_blocks > 1 ? J->sample_blocks : 1, blk = R > 1 ? J->sample_block : 0;
+    if (R > 1 && (J->variant == ORACLE_NODOF || blk < 0 || blk >= R || J->spp % R)) return -1;
+    const int spp_local = J->spp / R;
+    const float c0 = blk == 0 ? 13.0f : 0.0f, alpha = blk == 0 ? 255.0f : 0.0f;
+    uint32_t seeds[4] = {J->seeds[0], J->seeds[1], J->seeds[2], J->seeds[3]};
+    if (blk > 0) { const uint32_t h = oracle_randomize_id((uint32_t)blk); for (int k = 0; k < 4; ++k) seeds[k] ^= h; }
 #ifdef _OPENMP
     int nthreads = J->nthreads > 0 ? J->nthreads : omp_get_max_threads();
 #pragma omp parallel num_threads(nthreads)
@@ -459,9 +466,9 @@ int oracle_render(const oracle_job *J, uint8_t *rgba8, float *accum, uint32_t *r
                 size_t pix = (size_t)j * W + i;
                 if (J->variant != ORACLE_NODOF) {
                     /* base:224-240 */
-                    Rng rng = rng_seed(J->seeds, (uint32_t)(j * W + i));
-                    V3 c = v3(13.0f, 13.0f, 13.0f);
-                    for (int r = J->spp; r--;) {
+                    Rng rng = rng_seed(seeds, (uint32_t)(j * W + i));
+                    V3 c = v3(c0, c0, c0);
+                    for (int r = spp_local; r--;) {
                         V3 o, d;
                         camera_ray(J, &rng, i, j, &o, &d);
                         V3 s = sample(&S, o, d, &rng, &cnt);
@@ -497,7 +504,7 @@ int oracle_render(const oracle_job *J, uint8_t *rgba8, float *accum, uint32_t *r
                         }
                     col[0] = acc[0].x + 13.0f; col[1] = acc[0].y + 13.0f; col[2] = acc[0].z + 13.0f;
                 }
-                col[3] = 255.0f;
+                col[3] = J->variant == ORACLE_NODOF ? 255.0f : alpha;
                 if (accum) memcpy(accum + 4 * pix, col, sizeof(col));
                 if (rgba8)
                     for (int k = 0; k < 4; ++k) rgba8[4 * pix + k] = f2u8_rz_sat(col[k]);

@@ -72,6 +72,9 @@ typedef struct {
     /* bidir variant only: the buffer lightTracer filled, nvpl x (x y z intensity), in buffer order */
     const float *vpls;
     int32_t nvpl;
+    /* sample-range sharding (ptcuda.h pt_render_params.sample_block/sample_blocks): block b of R renders spp/R
+     * samples, scale 224/spp, seeds ^ randomizeId(b) and start value 0 / alpha 0 for b > 0.  0 or 1 = off. */
+    int32_t sample_block, sample_blocks;
 } oracle_job;
 
 /* Outputs may be NULL.  rgba8: W*H*4 bytes.  accum: W*H*4 floats (the value handed to

@@ -50,6 +50,7 @@ class oracle_job(C.Structure):
         ("cell_start", C.POINTER(C.c_uint32)), ("cell_refs", C.POINTER(C.c_uint32)),
         ("nthreads", C.c_int32),
         ("vpls", C.POINTER(C.c_float)), ("nvpl", C.c_int32),
+        ("sample_block", C.c_int32), ("sample_blocks", C.c_int32),
     ]
 
 
@@ -181,13 +182,14 @@ class OracleLib:
         return (vpl, rng) if want_rng else vpl
 
     def render(self, variant, width, height, seeds, scene, spp=64, rows=None, cam=None, grid=None, want_accum=True,
-               want_rng=True, nthreads=0, modifier=3.0, vpls=None, n_vlp=512):
+               want_rng=True, nthreads=0, modifier=3.0, vpls=None, n_vlp=512, sample_block=0, sample_blocks=0):
         """scene: dict with spheres, squares, triangles (n,12), lights (nl,4) [, box_min, box_max].
         bidir: `vpls` (n,4) is the lightTracer buffer; None runs light_tracer(seeds, scene, n_vlp) first, as the
         reference host does (CLSuperBidirectionalPathTracer.c:370-375: same seeds for both kernels)."""
         J = oracle_job()
         J.variant = VARIANTS[variant]
         J.width, J.height, J.spp = width, height, spp
+        J.sample_block, J.sample_blocks = int(sample_block), int(sample_blocks)
         if rows is not None:
             J.row_begin, J.row_end = rows
         tris = self._fill_scene(J, seeds, scene)

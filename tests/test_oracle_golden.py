@@ -175,3 +175,23 @@ def test_bidir_image_golden(oracle_sep, scene_dirs):
     host = json.loads(bytes(g["host_json"]).decode())["bidir"]
     assert sc["triangles"].shape[0] == host["ntriangles"] and sc["lights"].shape[0] == host["nlights"]
     assert int(host["vpl_print"]) == 512 * host["nlights"]
+
+
+def test_sample_blocks_definition(oracle_sep, scene_dirs):
+    """Sample-range sharding as the oracle states it (oracle.h): R = 1 is the plain render; block 0 walks the reference's
+    own stream; the blocks' float buffers sum to a frame with alpha 255 that matches the unsharded one statistically."""
+    sc = oracle_sep.load_scene_dir(scene_dirs["lmem"], "lmem")
+    rows = (344, 352)
+    full = oracle_sep.render("lmem", 512, 512, SEED_SETS[0], sc, rows=rows)
+    one = oracle_sep.render("lmem", 512, 512, SEED_SETS[0], sc, rows=rows, sample_block=0, sample_blocks=1)
+    assert np.array_equal(full["accum"].view(np.uint32), one["accum"].view(np.uint32))
+    parts = [oracle_sep.render("lmem", 512, 512, SEED_SETS[0], sc, rows=rows, sample_block=b, sample_blocks=4) for b in range(4)]
+    short = oracle_sep.render("lmem", 512, 512, SEED_SETS[0], sc, rows=rows, spp=16)
+    assert np.array_equal(parts[0]["rng_state"], short["rng_state"])
+    assert not np.array_equal(parts[1]["rng_state"], parts[2]["rng_state"])
+    total = sum(p["accum"][rows[0]:rows[1]] for p in parts)
+    assert (total[..., 3] == 255.0).all()
+    diff = np.clip(np.trunc(total[..., :3]), 0, 255) - np.clip(np.trunc(full["accum"][rows[0]:rows[1], :, :3]), 0, 255)
+    assert abs(diff.mean()) < 0.5 and np.sqrt((diff ** 2).mean()) < 14.0
+    with pytest.raises(ValueError):
+        oracle_sep.render("lmem", 64, 64, SEED_SETS[0], sc, sample_block=0, sample_blocks=3)
