@@ -35,12 +35,15 @@ PT_DEV const SceneBlock *stage_scene_smem(const LaunchArgs &P, unsigned char *sm
     return reinterpret_cast<const SceneBlock *>(smem);
 }
 
-// Work counters: warp shuffle-reduce, then ONE set of global atomics per CTA (and none for zero sums) —
-// the wavefront kernels call this once per launch, so per-warp atomics on seven shared addresses would
-// serialise in L2.  Must be reached by every thread of the CTA.
+// Work counters: warp shuffle-reduce, then native 32-bit shared-memory atomics per warp (a 64-bit shared atomicAdd
+// is a compare-and-swap loop: it was 6 % of the NoDoF kernel's instructions), then ONE set of 64-bit global atomics
+// per CTA (none for zero sums) — the wavefront kernels call this once per launch, so per-warp atomics on seven
+// global addresses would serialise in L2.  Per-CTA raw sums fit 32 bits (<= 1024 threads x u32 per-thread counters
+// that themselves stay far below 2^22 here); the products with the triangle / primitive counts are formed in 64 bits.
+// Must be reached by every thread of the CTA.
 PT_DEV void flush_counters(const LaunchArgs &P, const Counters &c, int ntri_counted, int nprims) {
-    __shared__ unsigned long long s_cnt[7];
-    if (threadIdx.x < 7) s_cnt[threadIdx.x] = 0ull;
+    __shared__ unsigned int s_raw[6];          // samples rays shadow cells gtri tri_loops
+    if (threadIdx.x < 6) s_raw[threadIdx.x] = 0u;
     __syncthreads();
     uint32_t rays = __reduce_add_sync(0xffffffffu, c.rays);
     uint32_t shadow = __reduce_add_sync(0xffffffffu, c.shadow);
@@ -49,20 +52,36 @@ PT_DEV void flush_counters(const LaunchArgs &P, const Counters &c, int ntri_coun
     uint32_t samples = __reduce_add_sync(0xffffffffu, c.samples);
     uint32_t loops = __reduce_add_sync(0xffffffffu, c.tri_loops);
     if ((threadIdx.x & 31) == 0) {
-        if (samples) atomicAdd(&s_cnt[0], (unsigned long long)samples);
-        if (rays) atomicAdd(&s_cnt[1], (unsigned long long)rays);
-        if (shadow) atomicAdd(&s_cnt[2], (unsigned long long)shadow);
-        if (gtri | rays) atomicAdd(&s_cnt[3], (unsigned long long)gtri + (unsigned long long)rays * ntri_counted);
-        if (cells) atomicAdd(&s_cnt[4], (unsigned long long)cells);
-        if (rays) atomicAdd(&s_cnt[5], (unsigned long long)rays * nprims);
-        if (gtri | loops) atomicAdd(&s_cnt[6], (unsigned long long)gtri + (unsigned long long)loops * ntri_counted);
+        if (samples) atomicAdd(&s_raw[0], samples);
+        if (rays) atomicAdd(&s_raw[1], rays);
+        if (shadow) atomicAdd(&s_raw[2], shadow);
+        if (cells) atomicAdd(&s_raw[3], cells);
+        if (gtri) atomicAdd(&s_raw[4], gtri);
+        if (loops) atomicAdd(&s_raw[5], loops);
     }
     __syncthreads();
-    if (threadIdx.x < 7 && P.counters && s_cnt[threadIdx.x]) atomicAdd(P.counters + threadIdx.x, s_cnt[threadIdx.x]);
+    if (threadIdx.x < 7 && P.counters) {
+        const unsigned long long r = s_raw[1], g = s_raw[4];
+        unsigned long long v;
+        switch (threadIdx.x) {
+            case 0: v = s_raw[0]; break;                                             // samples
+            case 1: v = r; break;                                                    // rays
+            case 2: v = s_raw[2]; break;                                             // shadow rays
+            case 3: v = g + r * (unsigned long long)ntri_counted; break;             // tri_tests (nominal)
+            case 4: v = s_raw[3]; break;                                             // cells visited
+            case 5: v = r * (unsigned long long)nprims; break;                       // prim_tests
+            default: v = g + (unsigned long long)s_raw[5] * (unsigned long long)ntri_counted; break;   // tri_tests executed
+        }
+        if (v) atomicAdd(P.counters + threadIdx.x, v);
+    }
 }
 
-template <int VARIANT, bool FMA, int MEM>
-__global__ void __launch_bounds__(128, VARIANT == PT_VARIANT_GRID ? 8 : 6) k_mega_pixel(const __grid_constant__ LaunchArgs P) {
+// BIG (trianglegrid on grids whose records do not stay in L1): 64 registers / 8 CTAs per SM and the two-trace form of
+// Sample(); otherwise 80 registers / 6 CTAs and the single ray loop (smaller code, instruction-cache resident).
+// Measured (B200): soup 1 M triangles 4.57 ms per 4 spp with BIG vs 4.87 without; default 96-triangle grid scene
+// 1.41 ms without vs 1.58 with.
+template <int VARIANT, bool FMA, int MEM, bool BIG>
+__global__ void __launch_bounds__(128, BIG ? 8 : 6) k_mega_pixel(const __grid_constant__ LaunchArgs P) {
     constexpr bool CARRY = VARIANT != PT_VARIANT_BASE;
     constexpr bool GRID = VARIANT == PT_VARIANT_GRID;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -79,7 +98,8 @@ __global__ void __launch_bounds__(128, VARIANT == PT_VARIANT_GRID ? 8 : 6) k_meg
         for (int s = 0; s < P.spp; ++s) {
             V3 o, d;
             camera_ray<FMA>(P.cam, rng, i, j, o, d);
-            V3 c = sample<FMA, CARRY, GRID>(P.ap, S, P.grid, o, d, rng, cnt);
+            V3 c = BIG ? sample_two_traces<FMA, CARRY, GRID>(P.ap, S, P.grid, o, d, rng, cnt)
+                       : sample<FMA, CARRY, GRID>(P.ap, S, P.grid, o, d, rng, cnt);
             cx = Ar<FMA>::madd(c.x, P.scale, cx);
             cy = Ar<FMA>::madd(c.y, P.scale, cy);
             cz = Ar<FMA>::madd(c.z, P.scale, cz);
@@ -92,7 +112,7 @@ __global__ void __launch_bounds__(128, VARIANT == PT_VARIANT_GRID ? 8 : 6) k_meg
     flush_counters(P, cnt, GRID ? 0 : S->ntri_counted, P.ap.nsq + P.ap.nsp);
 }
 
-template <bool FMA, int MEM>
+template <bool FMA, int MEM>     // 8 warps = a 4x2 pixel tile per CTA (4x1 tiles time the same, 2x1 tiles 3 % slower)
 __global__ void __launch_bounds__(256, 4) k_mega_nodof(const __grid_constant__ LaunchArgs P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const SceneBlock *S = (MEM == PT_SCENE_SMEM) ? stage_scene_smem(P, smem_raw) : &c_scene;
@@ -101,9 +121,11 @@ __global__ void __launch_bounds__(256, 4) k_mega_nodof(const __grid_constant__ L
     const int vr = blockIdx.y * 2 + (warp >> 2);
     Counters cnt = {0, 0, 0, 0, 0, 0};
     const int py = map_row(P, vr);
+    // (a grid-stride persistent form of this kernel — one resident wave of CTAs, warps striding over the pixels — was
+    // measured slower: 0.434 ms vs 0.409 ms; the hardware CTA scheduler balances the uneven pixels better)
     if (px < P.W && vr < P.nrows && py < P.row_end) {   // warp-uniform
-        float ax[2], ay[2], az[2];
-#pragma unroll
+        float ax = 0.f, ay = 0.f, az = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
+#pragma unroll 1                                                    // ONE copy of Sample(): the code stays i-cache resident
         for (int h = 0; h < 2; ++h) {
             const int li = lane + 32 * h;                       // local id inside the 8x8 group
             const int gi = 8 * px + (li & 7), gj = 8 * py + (li >> 3);
@@ -112,11 +134,12 @@ __global__ void __launch_bounds__(256, 4) k_mega_nodof(const __grid_constant__ L
             V3 o, d;
             camera_ray<FMA>(P.cam, rng, px, py, o, d);
             V3 c = sample<FMA, true, false>(P.ap, S, P.grid, o, d, rng, cnt);
-            ax[h] = __fmul_rn(c.x, 3.5f); ay[h] = __fmul_rn(c.y, 3.5f); az[h] = __fmul_rn(c.z, 3.5f);
+            if (h == 0) { ax = __fmul_rn(c.x, 3.5f); ay = __fmul_rn(c.y, 3.5f); az = __fmul_rn(c.z, 3.5f); }
+            else        { bx = __fmul_rn(c.x, 3.5f); by = __fmul_rn(c.y, 3.5f); bz = __fmul_rn(c.z, 3.5f); }
             if (P.rng_out) P.rng_out[gid] = make_uint4(rng.x0, rng.x1, rng.c0, rng.c1);
         }
         // nodof:253-274 reduction tree: li += li+32, then +16, +8, +4, +2, +1
-        float sx = __fadd_rn(ax[0], ax[1]), sy = __fadd_rn(ay[0], ay[1]), sz = __fadd_rn(az[0], az[1]);
+        float sx = __fadd_rn(ax, bx), sy = __fadd_rn(ay, by), sz = __fadd_rn(az, bz);
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             sx = __fadd_rn(sx, __shfl_down_sync(0xffffffffu, sx, off));
@@ -133,18 +156,24 @@ __global__ void __launch_bounds__(256, 4) k_mega_nodof(const __grid_constant__ L
     flush_counters(P, cnt, S->ntri_counted, P.ap.nsq + P.ap.nsp);
 }
 
-template <int VARIANT, bool FMA, int MEM>
-static int launch_pixel(pt_ctx ctx, const LaunchArgs &args_in) {
+template <int VARIANT, bool FMA, int MEM, bool BIG>
+static int launch_pixel_b(pt_ctx ctx, const LaunchArgs &args_in) {
     LaunchArgs args = args_in;
     args.ap.tri_coop = MEM == PT_SCENE_SMEM;
     dim3 grid((args.W + 15) / 16, (args.nrows + 7) / 8), block(128);
     size_t smem = MEM == PT_SCENE_SMEM ? (size_t)args.scene_bytes : 0;
     if (smem > 48 * 1024)
-        PT_CUDA(cudaFuncSetAttribute(k_mega_pixel<VARIANT, FMA, MEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+        PT_CUDA(cudaFuncSetAttribute(k_mega_pixel<VARIANT, FMA, MEM, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                 "opt-in shared memory");
-    k_mega_pixel<VARIANT, FMA, MEM><<<grid, block, smem, ctx->stream>>>(args);
+    k_mega_pixel<VARIANT, FMA, MEM, BIG><<<grid, block, smem, ctx->stream>>>(args);
     PT_CUDA(cudaGetLastError(), "launch k_mega_pixel");
     return 0;
+}
+
+template <int VARIANT, bool FMA, int MEM>
+static int launch_pixel(pt_ctx ctx, const LaunchArgs &args) {
+    if (VARIANT == PT_VARIANT_GRID && ctx->ntri_total > 16384) return launch_pixel_b<VARIANT, FMA, MEM, VARIANT == PT_VARIANT_GRID>(ctx, args);
+    return launch_pixel_b<VARIANT, FMA, MEM, false>(ctx, args);
 }
 
 template <bool FMA, int MEM>
