@@ -359,7 +359,8 @@ def bench_ours(args, w, wname):
     tmp = tempfile.TemporaryDirectory()
     d = scene_dir_for(w, tmp.name)
     scene = load_workload_scene(w, d)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()                 # a real stream (the legacy default stream cannot be graph-captured)
+    torch.cuda.set_stream(stream)
     r = pt.Renderer(device=local_rank, stream=stream.cuda_stream)
     r.set_scene(scene)
     if w["variant"] == "grid":

@@ -95,6 +95,11 @@ struct pt_ctx_s {
     // wavefront / persistent scratch
     void *d_scratch;
     size_t scratch_cap;
+    // wavefront: the ~500 launches of a frame captured once as a CUDA graph and replayed while nothing changes
+    cudaGraphExec_t wf_exec;
+    pt::LaunchArgs *wf_key_args;   // launch arguments the captured graph was built for (+ variant/arith/scratch below)
+    int wf_key_variant, wf_key_fma;
+    void *wf_key_scratch;
 };
 
 // internal helpers (ptcuda.cu)

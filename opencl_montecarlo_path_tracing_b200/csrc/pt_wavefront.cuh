@@ -275,8 +275,24 @@ static int launch_wavefront_v(pt_ctx ctx, const LaunchArgs &args) {
     B.tmp = NODOF ? (float4 *)(base + o_tmp) : nullptr;
     const unsigned blocks = (n + 255) / 256;
     cudaStream_t st = ctx->stream;
+    // A frame is ~8 small launches per pass x 64+ passes and is launch-bound.  None of them needs the host (queue
+    // lengths stay on the device), so the whole frame is captured ONCE into a CUDA graph and replayed with a single
+    // cudaGraphLaunch for as long as the launch arguments, variant, policy and scratch arena are unchanged
+    // (PT_WF_GRAPH=0 keeps the plain launches).
+    static int use_graph = -1;
+    if (use_graph < 0) { const char *e = getenv("PT_WF_GRAPH"); use_graph = e ? atoi(e) : 1; }
+    if (use_graph && ctx->wf_exec && ctx->wf_key_args && ctx->wf_key_variant == VARIANT && ctx->wf_key_fma == (int)FMA &&
+        ctx->wf_key_scratch == ctx->d_scratch && memcmp(ctx->wf_key_args, &args, sizeof(LaunchArgs)) == 0) {
+        PT_CUDA(cudaGraphLaunch(ctx->wf_exec, st), "replay wavefront graph");
+        return 0;
+    }
+    bool capturing = use_graph != 0;
+    if (capturing && cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        (void)cudaGetLastError();          // e.g. the legacy default stream cannot be captured: plain launches instead
+        capturing = false;
+    }
     for (int pass = 0; pass < passes; ++pass) {
-        PT_CUDA(cudaMemsetAsync(B.qcount, 0, 64 * 4, st), "reset queue counters");
+        cudaMemsetAsync(B.qcount, 0, 64 * 4, st);
         wf_generate<FMA, NODOF><<<blocks, 256, 0, st>>>(args, B, pass);
         wf_intersect<FMA, CARRY, GRID, false><<<blocks, 256, 0, st>>>(args, B, nullptr, nullptr);
         wf_shade<FMA, CARRY, GRID, NODOF, true><<<blocks, 256, 0, st>>>(args, B, pass, nullptr, nullptr, B.queue[0], B.qcount + 0);
@@ -288,7 +304,20 @@ static int launch_wavefront_v(pt_ctx ctx, const LaunchArgs &args) {
         if (NODOF && args.rng_out) wf_store_sample_rng<<<blocks, 256, 0, st>>>(args, B, pass);
     }
     wf_resolve<NODOF><<<blocks, 256, 0, st>>>(args, B);
-    PT_CUDA(cudaGetLastError(), "launch wavefront");
+    if (!capturing) {
+        PT_CUDA(cudaGetLastError(), "launch wavefront");
+        return 0;
+    }
+    cudaGraph_t graph = nullptr;
+    PT_CUDA(cudaStreamEndCapture(st, &graph), "end wavefront capture");
+    if (ctx->wf_exec) { cudaGraphExecDestroy(ctx->wf_exec); ctx->wf_exec = nullptr; }
+    cudaError_t ie = cudaGraphInstantiate(&ctx->wf_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { ctx->wf_exec = nullptr; return pt_cuda_fail(ie, "instantiate wavefront graph"); }
+    if (!ctx->wf_key_args) ctx->wf_key_args = (LaunchArgs *)malloc(sizeof(LaunchArgs));
+    memcpy(ctx->wf_key_args, &args, sizeof(LaunchArgs));
+    ctx->wf_key_variant = VARIANT; ctx->wf_key_fma = (int)FMA; ctx->wf_key_scratch = ctx->d_scratch;
+    PT_CUDA(cudaGraphLaunch(ctx->wf_exec, st), "launch wavefront graph");
     return 0;
 }
 

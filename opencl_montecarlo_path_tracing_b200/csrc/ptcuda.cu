@@ -133,6 +133,8 @@ extern "C" void pt_destroy(pt_ctx c) {
     cudaFree(c->d_cells); cudaFree(c->d_recs); cudaFree(c->d_refs); cudaFree(c->d_cell_start);
     cudaFree(c->d_rgba); cudaFree(c->d_accum); cudaFree(c->d_rng); cudaFree(c->d_counters); cudaFree(c->d_scratch);
     cudaFree(c->d_vpls); cudaFree(c->d_vpl_active); cudaFree(c->d_vpl_count);
+    if (c->wf_exec) cudaGraphExecDestroy(c->wf_exec);
+    free(c->wf_key_args);
     if (c->h_rgba) cudaFreeHost(c->h_rgba);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     free(c);
