@@ -12,4 +12,4 @@ with pt.Renderer(0) as r:
     for (w, h) in ((512, 512), (1920, 1080)):
         for mem in ("smem", "const"):
             best = min(r.render("bidir", w, h, (1, 2, 3, 4), scene_mem=mem, read_image=False).ms for _ in range(6))
-            print("BT", os.environ.get("PT_BIDIR_BT"), w, h, mem, "render %.3f ms  light %.4f ms" % (best, lt), flush=True)
+            print("bidir", w, h, mem, "render %.3f ms  light %.4f ms" % (best, lt), flush=True)
