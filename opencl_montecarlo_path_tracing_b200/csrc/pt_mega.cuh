@@ -42,7 +42,7 @@ PT_DEV const SceneBlock *stage_scene_smem(const LaunchArgs &P, unsigned char *sm
 // that themselves stay far below 2^22 here); the products with the triangle / primitive counts are formed in 64 bits.
 // Must be reached by every thread of the CTA.
 PT_DEV void flush_counters(const LaunchArgs &P, const Counters &c, int ntri_counted, int nprims) {
-    __shared__ unsigned int s_raw[6];          // samples rays shadow cells gtri tri_loops
+    __shared__ unsigned int s_raw[6];          // samples rays shadow cells gtri btests
     if (threadIdx.x < 6) s_raw[threadIdx.x] = 0u;
     __syncthreads();
     uint32_t rays = __reduce_add_sync(0xffffffffu, c.rays);
@@ -50,7 +50,7 @@ PT_DEV void flush_counters(const LaunchArgs &P, const Counters &c, int ntri_coun
     uint32_t cells = __reduce_add_sync(0xffffffffu, c.cells);
     uint32_t gtri = __reduce_add_sync(0xffffffffu, c.gtri);
     uint32_t samples = __reduce_add_sync(0xffffffffu, c.samples);
-    uint32_t loops = __reduce_add_sync(0xffffffffu, c.tri_loops);
+    uint32_t loops = __reduce_add_sync(0xffffffffu, c.btests);
     if ((threadIdx.x & 31) == 0) {
         if (samples) atomicAdd(&s_raw[0], samples);
         if (rays) atomicAdd(&s_raw[1], rays);
@@ -70,18 +70,19 @@ PT_DEV void flush_counters(const LaunchArgs &P, const Counters &c, int ntri_coun
             case 3: v = g + r * (unsigned long long)ntri_counted; break;             // tri_tests (nominal)
             case 4: v = s_raw[3]; break;                                             // cells visited
             case 5: v = r * (unsigned long long)nprims; break;                       // prim_tests
-            default: v = g + (unsigned long long)s_raw[5] * (unsigned long long)ntri_counted; break;   // tri_tests executed
+            default: v = g + (unsigned long long)s_raw[5]; break;                     // tri_tests executed (grid + brute force)
         }
         if (v) atomicAdd(P.counters + threadIdx.x, v);
     }
 }
 
-// BIG (trianglegrid on grids whose records do not stay in L1): 64 registers / 8 CTAs per SM and the two-trace form of
+// BIG, trianglegrid: grids whose records do not stay in L1 — 64 registers / 8 CTAs per SM and the two-trace form of
 // Sample(); otherwise 80 registers / 6 CTAs and the single ray loop (smaller code, instruction-cache resident).
+// BIG, brute-force variants: frames above 400 k pixels — per-cluster triangle culling compiled in (tri_loop<.., CL>).
 // Measured (B200): soup 1 M triangles 4.57 ms per 4 spp with BIG vs 4.87 without; default 96-triangle grid scene
 // 1.41 ms without vs 1.58 with.
 template <int VARIANT, bool FMA, int MEM, bool BIG>
-__global__ void __launch_bounds__(128, BIG ? 8 : 6) k_mega_pixel(const __grid_constant__ LaunchArgs P) {
+__global__ void __launch_bounds__(128, (BIG && VARIANT == PT_VARIANT_GRID) ? 8 : 6) k_mega_pixel(const __grid_constant__ LaunchArgs P) {
     constexpr bool CARRY = VARIANT != PT_VARIANT_BASE;
     constexpr bool GRID = VARIANT == PT_VARIANT_GRID;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -98,8 +99,8 @@ __global__ void __launch_bounds__(128, BIG ? 8 : 6) k_mega_pixel(const __grid_co
         for (int s = 0; s < P.spp; ++s) {
             V3 o, d;
             camera_ray<FMA>(P.cam, rng, i, j, o, d);
-            V3 c = BIG ? sample_two_traces<FMA, CARRY, GRID>(P.ap, S, P.grid, o, d, rng, cnt)
-                       : sample<FMA, CARRY, GRID>(P.ap, S, P.grid, o, d, rng, cnt);
+            V3 c = (BIG && GRID) ? sample_two_traces<FMA, CARRY, GRID>(P.ap, S, P.grid, o, d, rng, cnt)
+                                 : sample<FMA, CARRY, GRID, BIG && !GRID>(P.ap, S, P.grid, o, d, rng, cnt);
             cx = Ar<FMA>::madd(c.x, P.scale, cx);
             cy = Ar<FMA>::madd(c.y, P.scale, cy);
             cz = Ar<FMA>::madd(c.z, P.scale, cz);
@@ -172,7 +173,7 @@ static int launch_pixel_b(pt_ctx ctx, const LaunchArgs &args_in) {
 
 template <int VARIANT, bool FMA, int MEM>
 static int launch_pixel(pt_ctx ctx, const LaunchArgs &args) {
-    if (VARIANT == PT_VARIANT_GRID && ctx->ntri_total > 16384) return launch_pixel_b<VARIANT, FMA, MEM, VARIANT == PT_VARIANT_GRID>(ctx, args);
+    if (VARIANT == PT_VARIANT_GRID ? ctx->ntri_total > 16384 : args.ap.ncl > 0) return launch_pixel_b<VARIANT, FMA, MEM, true>(ctx, args);
     return launch_pixel_b<VARIANT, FMA, MEM, false>(ctx, args);
 }
 

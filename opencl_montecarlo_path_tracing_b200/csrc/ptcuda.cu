@@ -220,6 +220,7 @@ extern "C" int pt_set_scene(pt_ctx c, const pt_scene *sc) {
     }
     const int nbrute = sc->ntriangles < PT_MAX_CONST_TRIS ? sc->ntriangles : PT_MAX_CONST_TRIS;
     int kept = 0;
+    int kept_src[PT_MAX_CONST_TRIS];            // source triangle of each kept record
     for (int a = 0; a < 2; ++a) {
         const bool fma = a == PT_ARITH_FMA;
         SceneBlock *S = c->h_scene[a];
@@ -245,9 +246,35 @@ extern "C" int pt_set_scene(pt_ctx c, const pt_scene *sc) {
             S->tri[3 * kept + 0] = make_float4(e2.x, e2.y, e2.z, e0.x);
             S->tri[3 * kept + 1] = make_float4(e0.y, e0.z, t[0], t[1]);
             S->tri[3 * kept + 2] = make_float4(t[2], n.x, n.y, n.z);
+            kept_src[kept] = i;
             ++kept;
         }
         S->ntri = kept;
+        // bounding sphere of every cluster of PT_CLUSTER consecutive records (double precision, radius inflated by
+        // 1 % + 0.01 exactly like the whole-mesh sphere below)
+        S->ncl = (kept + PT_CLUSTER - 1) / PT_CLUSTER;
+        for (int cl = 0; cl < S->ncl; ++cl) {
+            double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+            const int k0 = cl * PT_CLUSTER, k1 = k0 + PT_CLUSTER < kept ? k0 + PT_CLUSTER : kept;
+            for (int k = k0; k < k1; ++k)
+                for (int v = 0; v < 3; ++v)
+                    for (int ax = 0; ax < 3; ++ax) {
+                        double x = sc->triangles[12 * (size_t)kept_src[k] + 4 * v + ax];
+                        if (x < lo[ax]) lo[ax] = x;
+                        if (x > hi[ax]) hi[ax] = x;
+                    }
+            double ctr[3], r2 = 0;
+            for (int ax = 0; ax < 3; ++ax) ctr[ax] = 0.5 * (lo[ax] + hi[ax]);
+            for (int k = k0; k < k1; ++k)
+                for (int v = 0; v < 3; ++v) {
+                    const float *q = sc->triangles + 12 * (size_t)kept_src[k] + 4 * v;
+                    double dx = q[0] - ctr[0], dy = q[1] - ctr[1], dz = q[2] - ctr[2];
+                    double d2 = dx * dx + dy * dy + dz * dz;
+                    if (d2 > r2) r2 = d2;
+                }
+            double rr = sqrt(r2) * 1.01 + 0.01;
+            S->csph[cl] = make_float4((float)ctr[0], (float)ctr[1], (float)ctr[2], isfinite(rr) ? (float)rr : INFINITY);
+        }
     }
     c->scene_bytes = (int)(offsetof(SceneBlock, tri) + (size_t)kept * 48);
     {
@@ -491,6 +518,17 @@ static int fill_args(pt_ctx c, const pt_camera *cam, const pt_render_params *p, 
     A->ap.mesh_cx = c->mesh_c[0]; A->ap.mesh_cy = c->mesh_c[1]; A->ap.mesh_cz = c->mesh_c[2];
     A->ap.mesh_r = p->no_cull ? INFINITY : c->mesh_r;
     A->ap.mesh_k = c->mesh_k;
+    {
+        // Per-cluster culling removes 60-70 % of the triangle tests of a ray that passes the mesh sphere, but adds a
+        // serial chain of sphere tests to it.  Large frames are throughput-bound and gain (1080p x 1024 spp: torus
+        // 79.9 -> 70.8 ms, 96-triangle mesh 90.6 -> 84.2 ms); small frames are bound by the serial sample chain of
+        // their heaviest pixels and lose 8-11 % (512x512: 1.85 -> 2.01 ms).  Same threshold as the kernel choice.
+        const long long pixels = (long long)p->width * (long long)(re - rb);
+        static int force = -2;
+        if (force == -2) { const char *e = getenv("PT_CLUSTER_CULL"); force = e ? atoi(e) : -1; }
+        const bool on = force >= 0 ? force != 0 : pixels > 400000;
+        A->ap.ncl = (p->no_cull || !on) ? 0 : hs->ncl;
+    }
     {
         // bounding box of all squares (x in [k-1,k+1], |y| <= 1, z = 4+j) and unit spheres (centre (k,0,j+4))
         float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};

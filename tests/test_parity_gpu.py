@@ -261,16 +261,19 @@ def test_conservative_culls_change_nothing(renderer, scene_dirs, arith):
     """Mesh bounding-sphere cull, analytic bounding-box cull (incl. their distance-proportional margins for the
     reference's far-field rounding): with and without them the float accumulation buffer is bit-identical,
     on whole frames that include the horizon, at two image sizes."""
-    for variant in ("base", "lmem", "nodof", "grid"):
-        scene = pt.load_scene_dir(scene_dirs[variant], variant)
+    for variant, sdir in (("base", "base"), ("lmem", "lmem"), ("nodof", "nodof"), ("grid", "grid"), ("base", "torus"), ("bidir", "bidir")):
+        scene = pt.load_scene_dir(scene_dirs[sdir], variant)
         renderer.set_scene(scene)
         if variant == "grid":
             renderer.build_grid(pt.grid_dims(scene))
+        if variant == "bidir":
+            renderer.light_tracer(SEED_SETS[1], 512, arith=arith)
+        # frames above 400 k pixels additionally run the per-cluster triangle cull (8 consecutive records per cluster)
         for (W, H, spp) in ((512, 512, 64), (1920, 1080, 64 if variant == "nodof" else 8)):
             a = renderer.render(variant, W, H, SEED_SETS[1], spp=spp, arith=arith, want_accum=True, cull=True)
             b = renderer.render(variant, W, H, SEED_SETS[1], spp=spp, arith=arith, want_accum=True, cull=False)
             bad = int((a.accum.view(np.uint32) != b.accum.view(np.uint32)).any(axis=2).sum())
             assert bad == 0, "%s %dx%d %s: %d pixels change when the conservative culls are enabled" % (variant, W, H, arith, bad)
             assert a.counters["rays"] == b.counters["rays"]
-            if variant in ("base", "lmem"):
+            if variant in ("base", "lmem", "bidir"):
                 assert a.counters["tri_tests_executed"] < b.counters["tri_tests_executed"] == b.counters["tri_tests"]
