@@ -190,17 +190,25 @@ int pt_grid_build_device(pt_ctx ctx, const pt_grid *g) {
     }
     G.cells = nullptr; G.recs = nullptr;
 
-    cudaFree(ctx->d_cells); cudaFree(ctx->d_recs); cudaFree(ctx->d_refs); cudaFree(ctx->d_cell_start);
-    ctx->d_cells = nullptr; ctx->d_recs = nullptr; ctx->d_refs = nullptr; ctx->d_cell_start = nullptr;
-
-    uint32_t *d_count = nullptr, *d_raw_start = nullptr, *d_cursor = nullptr, *d_raw_refs = nullptr, *d_bsums = nullptr;
+    // All buffers of the build live in the context and only ever grow: cudaMalloc / cudaFree of the ~250 MB a 1 M-
+    // triangle grid needs cost 80 ms per build, 300x the 0.24 ms the nine kernels take.
     const int nblocks = (int)((ncells + SCAN_BLOCK - 1) / SCAN_BLOCK);
-    PT_CUDA(cudaMalloc(&d_count, ncells * 4), "alloc grid count");
-    PT_CUDA(cudaMalloc(&d_raw_start, (ncells + 1) * 4), "alloc grid start");
-    PT_CUDA(cudaMalloc(&d_cursor, ncells * 4), "alloc grid cursor");
-    PT_CUDA(cudaMalloc(&d_bsums, (size_t)(nblocks + 1) * 4), "alloc scan sums");
-    PT_CUDA(cudaMalloc(&ctx->d_cell_start, (ncells + 1) * 4), "alloc cell_start");
-    PT_CUDA(cudaMalloc(&ctx->d_cells, ncells * sizeof(uint2)), "alloc cells");
+    auto grow = [&](void **ptr, size_t *capacity, size_t bytes, const char *what) -> int {
+        if (*ptr && *capacity >= bytes) return 0;
+        if (*ptr) cudaFree(*ptr);
+        *ptr = nullptr;
+        *capacity = 0;
+        PT_CUDA(cudaMalloc(ptr, bytes), what);
+        *capacity = bytes;
+        return 0;
+    };
+    if (grow((void **)&ctx->gb_count, &ctx->gb_cap[0], ncells * 4, "alloc grid count")) return 1;
+    if (grow((void **)&ctx->gb_raw_start, &ctx->gb_cap[1], (ncells + 1) * 4, "alloc grid start")) return 1;
+    if (grow((void **)&ctx->gb_cursor, &ctx->gb_cap[2], ncells * 4, "alloc grid cursor")) return 1;
+    if (grow((void **)&ctx->gb_bsums, &ctx->gb_cap[3], (size_t)(nblocks + 1) * 4, "alloc scan sums")) return 1;
+    if (grow((void **)&ctx->d_cell_start, &ctx->gb_cap[4], (ncells + 1) * 4, "alloc cell_start")) return 1;
+    if (grow((void **)&ctx->d_cells, &ctx->gb_cap[5], ncells * sizeof(uint2), "alloc cells")) return 1;
+    uint32_t *d_count = ctx->gb_count, *d_raw_start = ctx->gb_raw_start, *d_cursor = ctx->gb_cursor, *d_bsums = ctx->gb_bsums;
     PT_CUDA(cudaMemsetAsync(d_count, 0, ncells * 4, ctx->stream), "memset");
     PT_CUDA(cudaMemsetAsync(d_cursor, 0, ncells * 4, ctx->stream), "memset");
 
@@ -215,9 +223,10 @@ int pt_grid_build_device(pt_ctx ctx, const pt_grid *g) {
     PT_CUDA(cudaMemcpyAsync(&raw_total, d_raw_start + ncells, 4, cudaMemcpyDeviceToHost, ctx->stream), "read total");
     PT_CUDA(cudaMemcpyAsync(&cap_total, ctx->d_cell_start + ncells, 4, cudaMemcpyDeviceToHost, ctx->stream), "read total");
     PT_CUDA(cudaStreamSynchronize(ctx->stream), "sync grid totals");
-    PT_CUDA(cudaMalloc(&d_raw_refs, (size_t)(raw_total ? raw_total : 1) * 4), "alloc raw refs");
-    PT_CUDA(cudaMalloc(&ctx->d_refs, (size_t)(cap_total ? cap_total : 1) * 4), "alloc refs");
-    PT_CUDA(cudaMalloc(&ctx->d_recs, (size_t)(cap_total ? cap_total : 1) * 3 * sizeof(float4)), "alloc records");
+    if (grow((void **)&ctx->gb_raw_refs, &ctx->gb_cap[6], (size_t)(raw_total ? raw_total : 1) * 4, "alloc raw refs")) return 1;
+    if (grow((void **)&ctx->d_refs, &ctx->gb_cap[7], (size_t)(cap_total ? cap_total : 1) * 4, "alloc refs")) return 1;
+    if (grow((void **)&ctx->d_recs, &ctx->gb_cap[8], (size_t)(cap_total ? cap_total : 1) * 3 * sizeof(float4), "alloc records")) return 1;
+    uint32_t *d_raw_refs = ctx->gb_raw_refs;
     if (ntri > 0) {
         k_grid_fill<<<tg, tb, 0, ctx->stream>>>(ctx->d_tris_raw, ntri, G, d_raw_start, d_cursor, d_raw_refs);
         PT_CUDA(cudaGetLastError(), "grid fill");
@@ -226,8 +235,7 @@ int pt_grid_build_device(pt_ctx ctx, const pt_grid *g) {
                                                                         ctx->d_cell_start, ctx->d_refs, ctx->d_recs,
                                                                         ctx->d_cells);
     PT_CUDA(cudaGetLastError(), "grid emit");
-    PT_CUDA(cudaStreamSynchronize(ctx->stream), "sync grid build");
-    cudaFree(d_count); cudaFree(d_raw_start); cudaFree(d_cursor); cudaFree(d_raw_refs); cudaFree(d_bsums);
+    // no synchronisation here: the render that follows is ordered behind the build on the same stream
 
     G.cells = ctx->d_cells;
     G.recs = ctx->d_recs;

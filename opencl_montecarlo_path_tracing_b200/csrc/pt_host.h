@@ -73,6 +73,8 @@ struct pt_ctx_s {
     uint32_t *d_cell_start;       // ncells + 1
     uint64_t total_refs;
     size_t ncells;
+    uint32_t *gb_count, *gb_raw_start, *gb_cursor, *gb_bsums, *gb_raw_refs;   // build scratch, kept between builds
+    size_t gb_cap[9];             // capacities (bytes) of the five scratch buffers, cell_start, cells, refs, recs
 
     // render targets owned by the context
     uint32_t *d_rgba;

@@ -131,6 +131,7 @@ extern "C" void pt_destroy(pt_ctx c) {
     }
     cudaFree(c->d_tris_raw);
     cudaFree(c->d_cells); cudaFree(c->d_recs); cudaFree(c->d_refs); cudaFree(c->d_cell_start);
+    cudaFree(c->gb_count); cudaFree(c->gb_raw_start); cudaFree(c->gb_cursor); cudaFree(c->gb_bsums); cudaFree(c->gb_raw_refs);
     cudaFree(c->d_rgba); cudaFree(c->d_accum); cudaFree(c->d_rng); cudaFree(c->d_counters); cudaFree(c->d_scratch);
     cudaFree(c->d_vpls); cudaFree(c->d_vpl_active); cudaFree(c->d_vpl_count);
     if (c->wf_exec) cudaGraphExecDestroy(c->wf_exec);
