@@ -118,3 +118,34 @@ def test_bad_arguments_are_rejected(renderer, scene_dirs):
         renderer.render("grid", 64, 64, SEED_SETS[0])                  # no grid built
     with pytest.raises(pt.PtError):
         renderer.render("base", 0, 64, SEED_SETS[0])
+
+
+def test_config5_frame_size_tiling_and_flavour_properties(renderer):
+    """BASELINE config 5's frame size (3840x2160) on a triangle soup through the grid: too big for the oracle, so the
+    size-independent properties are checked instead — three row bands and 3-rank interleaved stripes compose to exactly
+    the whole-frame render, and the persistent flavour agrees (accumulation buffer and final RNG states)."""
+    import gen_mesh
+    tris = gen_mesh.soup(70000, box_size=30.0)
+    lo, hi = gen_mesh.bbox_like_reference(tris)
+    scene = pt.Scene(np.array([1024, 0, 0, 0, 145, 0, 0, 2048, 0], np.int32), np.array([4096, 0, 0, 0, 0, 0, 129, 0, 8192], np.int32),
+                     tris, np.array([[10, 4, 10, 400], [15, 2, 7, 300]], np.float32), lo, hi)
+    renderer.set_scene(scene)
+    renderer.build_grid(pt.grid_dims(scene))
+    W, H, spp = 3840, 2160, 2
+    whole = renderer.render("grid", W, H, (1, 2, 3, 4), spp=spp, want_accum=True, want_rng=True)
+    assert whole.counters["samples"] == W * H * spp and (whole.image[..., 3] == 255).all()
+    acc = np.zeros_like(whole.accum)
+    for rows in ((0, 700), (700, 1500), (1500, 2160)):
+        part = renderer.render("grid", W, H, (1, 2, 3, 4), spp=spp, rows=rows, want_accum=True)
+        acc[rows[0]:rows[1]] = part.accum[rows[0]:rows[1]]
+    assert np.array_equal(acc.view(np.uint32), whole.accum.view(np.uint32))
+    acc = np.zeros_like(whole.accum)
+    rays = 0
+    for rank in range(3):
+        part = renderer.render("grid", W, H, (1, 2, 3, 4), spp=spp, interleave=8, rank=rank, nranks=3, want_accum=True)
+        acc += part.accum                                   # rows a rank does not own stay zero: the sum is exact
+        rays += part.counters["rays"]
+    assert np.array_equal(acc.view(np.uint32), whole.accum.view(np.uint32)) and rays == whole.counters["rays"]
+    other = renderer.render("grid", W, H, (1, 2, 3, 4), spp=spp, kernel="persistent", want_accum=True, want_rng=True)
+    assert np.array_equal(other.accum.view(np.uint32), whole.accum.view(np.uint32))
+    assert np.array_equal(other.rng_state, whole.rng_state)
