@@ -1,0 +1,48 @@
+"""bench.py's reference arm runs on the CPU, so its JSON contract can be checked here; the committed bench lines of
+our own arm (profiles/) are checked for the keys the contract names."""
+import glob
+import json
+import os
+import subprocess
+import sys
+
+from conftest import ROOT
+
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+             "dtype", "data", "config", "e2e", "gpu_launches"}
+
+
+def test_reference_arm_prints_one_contract_line():
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert BASE_KEYS <= set(j) and j["impl"] == "reference" and j["vs_baseline"] is None
+    assert j["metric"] == "Mrays/s" and j["unit"] == "Mrays/s" and j["higher_is_better"] is True and j["value"] > 0
+    assert j["config"]["workload"] == "nodof_512x512x64"
+    assert j["cpu_baseline"]["kind"] in ("reference", "port") and j["cpu_baseline"]["cores"] >= 1 and j["cpu_baseline"]["value"] == j["value"]
+    assert j["e2e"] == {"value": j["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_other_ranks_stay_silent():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
+    assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+def test_committed_bench_lines_follow_the_contract():
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r1_2*_bench_*.json")) + glob.glob(os.path.join(ROOT, "profiles", "r1_17_bench_*.json")))
+    assert files
+    for f in files:
+        j = json.loads(open(f).read().strip().splitlines()[-1])
+        assert BASE_KEYS <= set(j), f
+        assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(j["e2e"]), f
+        assert j["e2e"]["h2d_bytes_per_step"] > 0 and j["e2e"]["d2h_bytes_per_step"] > 0, f
+        assert j["gpu_launches"] > 0 and j["warmup"] >= 3, f
+        assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(j["clocks"]), f
+        assert not set(j["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}, f
+        assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(j["roofline"]), f
+        assert "workload" in j["config"] and "l2" in j["config"], f
