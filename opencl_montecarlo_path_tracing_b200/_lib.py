@@ -68,6 +68,7 @@ class pt_render_params(C.Structure):
         ("sample_block", C.c_int32),
         ("sample_blocks", C.c_int32),
         ("n_vlp", C.c_int32),
+        ("cluster_cull", C.c_int32),
     ]
 
 
@@ -141,6 +142,7 @@ PTCUDA_SYMBOLS = {
     "pt_probe_trace": (_I, [_VP, _I, _I, _I, _FP, _FP, _FP, _I32P, _FP]),
     "pt_selftest_fastmath": (_I, [_VP, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)]),
     "pt_probe_rng": (_I, [_VP, _U32P, C.c_uint32, _I, _FP, _U32P]),
+    "pt_measure_peaks": (_I, [_VP, C.POINTER(C.c_double)]),
 }
 
 PTHOST_SYMBOLS = {

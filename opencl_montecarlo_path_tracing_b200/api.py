@@ -161,7 +161,8 @@ class RenderResult:
 
 
 def make_params(variant, width, height, seeds, spp=64, kernel="auto", scene_mem=None, arith="fma", rows=None,
-                want_accum=False, want_rng=False, interleave=0, rank=0, nranks=1, cull=True, n_vlp=0, sample_block=0, sample_blocks=0):
+                want_accum=False, want_rng=False, interleave=0, rank=0, nranks=1, cull=True, n_vlp=0, sample_block=0, sample_blocks=0,
+                cluster_cull="auto"):
     p = pt_render_params()
     p.variant = PT_VARIANT[variant]
     p.width, p.height, p.spp = int(width), int(height), int(spp)
@@ -178,6 +179,7 @@ def make_params(variant, width, height, seeds, spp=64, kernel="auto", scene_mem=
     p.no_cull = 0 if cull else 1
     p.n_vlp = int(n_vlp)
     p.sample_block, p.sample_blocks = int(sample_block), int(sample_blocks)
+    p.cluster_cull = {"auto": 0, "on": 1, "off": 2}[cluster_cull]
     return p
 
 
@@ -335,6 +337,12 @@ class Renderer:
         out = (C.c_uint64 * 3)()
         _check(self._l.pt_selftest_fastmath(self.ctx, int(npairs), int(seed), out), "pt_selftest_fastmath")
         return {"div_mismatches": int(out[0]), "sqrt_mismatches": int(out[1]), "pairs_tested": int(out[2])}
+
+    def measure_peaks(self):
+        """Measured FP32 / issue-slot peaks of this device (pt_measure_peaks)."""
+        out = (C.c_double * 4)()
+        _check(self._l.pt_measure_peaks(self.ctx, out), "pt_measure_peaks")
+        return {"fp32_tflops": out[0], "ffma_gwarp_inst_per_s": out[1], "mixed_gwarp_inst_per_s": out[2], "mixed_kernel_ms": out[3]}
 
     def probe_rng(self, seeds, gid, nsteps):
         s = (C.c_uint32 * 4)(*[int(v) for v in seeds])

@@ -85,7 +85,8 @@ struct pt_ctx_s {
     size_t h_rgba_cap;
     unsigned long long *d_counters;
     int last_w, last_h, last_variant;
-    size_t last_rng_items;
+    int accum_valid_w, accum_valid_h;   // extent of d_accum the most recent launch wrote (0: it did not request it)
+    size_t rng_valid_items;             // work-items of d_rng the most recent launch wrote
 
     // bidirectional variant: VPL buffer as the reference defines it + its compacted non-zero entries
     bool vpls_set;

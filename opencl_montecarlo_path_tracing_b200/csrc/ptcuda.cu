@@ -11,6 +11,7 @@
 #include <dlfcn.h>
 
 #include <atomic>
+#include <mutex>
 #include <new>
 
 #include "pt_host.h"
@@ -23,7 +24,7 @@
 #include "pt_gridstream.cuh"
 
 // ------------------------------------------------------------------------------------ errors
-static int g_error_mode = PT_ERRORS_EXIT;
+static std::atomic<int> g_error_mode{PT_ERRORS_EXIT};
 static thread_local char g_last_error[1024] = "";
 
 extern "C" void pt_set_error_mode(int mode) { g_error_mode = mode; }
@@ -118,13 +119,24 @@ extern "C" pt_ctx pt_create_on_stream(int device, void *cuda_stream) {
 
 struct ConstOwner { pt_ctx owner; uint64_t version; int arith; };
 static ConstOwner g_const_owner[64];
+// The __constant__ scene block is ONE per device, shared by every context on it.  Rebinding it and the launch that reads it
+// must not interleave with another host thread doing the same for a different context on that device: both happen under
+// this per-device lock (dispatch(), pt_probe_trace, pt_launch_lighttracer), and a change of owner first drains the device.
+static std::recursive_mutex g_dev_lock[64];
+struct DevLock {
+    std::unique_lock<std::recursive_mutex> lk;
+    explicit DevLock(int device) { if (device >= 0 && device < 64) lk = std::unique_lock<std::recursive_mutex>(g_dev_lock[device]); }
+};
 static std::atomic<uint64_t> g_scene_version{1};
 
 extern "C" void pt_destroy(pt_ctx c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    if (c->device < 64 && g_const_owner[c->device].owner == c) g_const_owner[c->device].owner = nullptr;
+    {
+        DevLock lock(c->device);
+        if (c->device < 64 && g_const_owner[c->device].owner == c) g_const_owner[c->device].owner = nullptr;
+    }
     for (int a = 0; a < 2; ++a) {
         if (c->h_scene[a]) cudaFreeHost(c->h_scene[a]);
         cudaFree(c->d_scene[a]);
@@ -334,6 +346,7 @@ extern "C" int pt_set_scene(pt_ctx c, const pt_scene *sc) {
 
 int pt_bind_const_scene(pt_ctx c, int arith) {
     if (c->device >= 64) return pt_fail(1, "device index too large");
+    DevLock lock(c->device);
     ConstOwner &o = g_const_owner[c->device];
     if (o.owner == c && o.version == c->scene_version && o.arith == arith) return 0;
     if (o.owner && o.owner != c) PT_CUDA(cudaDeviceSynchronize(), "sync before rebinding constant scene");
@@ -399,10 +412,14 @@ extern "C" pt_event pt_build_grid(pt_ctx c, const pt_grid *g) {
 }
 
 extern "C" int pt_read_grid_csr(pt_ctx c, uint32_t *cell_start, uint32_t *refs, uint64_t *total_refs) {
-    if (!c->grid_set) return pt_fail(1, "pt_read_grid_csr: no grid built");
+    if (!c || !c->grid_set) return pt_fail(1, "pt_read_grid_csr: no grid built");
     if (total_refs) *total_refs = c->total_refs;
-    if (cell_start) PT_CUDA(cudaMemcpy(cell_start, c->d_cell_start, (c->ncells + 1) * 4, cudaMemcpyDeviceToHost), "read cell_start");
-    if (refs && c->total_refs) PT_CUDA(cudaMemcpy(refs, c->d_refs, c->total_refs * 4, cudaMemcpyDeviceToHost), "read refs");
+    // The build leaves its last kernels unsynchronised on the context's (non-blocking) stream: read on THAT stream and
+    // wait for it, like pt_read_accum / pt_read_vpls (the legacy default stream would not wait for it).
+    PT_CUDA(cudaSetDevice(c->device), "select device");
+    if (cell_start) PT_CUDA(cudaMemcpyAsync(cell_start, c->d_cell_start, (c->ncells + 1) * 4, cudaMemcpyDeviceToHost, c->stream), "read cell_start");
+    if (refs && c->total_refs) PT_CUDA(cudaMemcpyAsync(refs, c->d_refs, c->total_refs * 4, cudaMemcpyDeviceToHost, c->stream), "read refs");
+    PT_CUDA(cudaStreamSynchronize(c->stream), "sync grid read");
     return 0;
 }
 
@@ -524,10 +541,12 @@ static int fill_args(pt_ctx c, const pt_camera *cam, const pt_render_params *p, 
         // serial chain of sphere tests to it.  Large frames are throughput-bound and gain (1080p x 1024 spp: torus
         // 79.9 -> 70.8 ms, 96-triangle mesh 90.6 -> 84.2 ms); small frames are bound by the serial sample chain of
         // their heaviest pixels and lose 8-11 % (512x512: 1.85 -> 2.01 ms).  Same threshold as the kernel choice.
-        const long long pixels = (long long)p->width * (long long)(re - rb);
+        const long long pixels = (long long)p->width * (long long)A->nrows;     // THIS launch's share of the frame (rows / stripes)
         static int force = -2;
         if (force == -2) { const char *e = getenv("PT_CLUSTER_CULL"); force = e ? atoi(e) : -1; }
-        const bool on = force >= 0 ? force != 0 : pixels > 400000;
+        bool on = force >= 0 ? force != 0 : pixels > 400000;
+        if (p->cluster_cull == PT_CLUSTER_CULL_ON) on = true;
+        if (p->cluster_cull == PT_CLUSTER_CULL_OFF) on = false;
         A->ap.ncl = (p->no_cull || !on) ? 0 : hs->ncl;
     }
     {
@@ -557,7 +576,7 @@ static int fill_args(pt_ctx c, const pt_camera *cam, const pt_render_params *p, 
 }
 
 // PT_KERNEL_AUTO / PT_SCENE_AUTO: measured best per variant on B200
-static pt_render_params resolve_auto(const pt_render_params *in) {
+static pt_render_params resolve_auto(const pt_render_params *in, int nrows) {
     pt_render_params p = *in;
     if (p.kernel == PT_KERNEL_AUTO) {
         if (p.variant == PT_VARIANT_BIDIR) p.kernel = PT_KERNEL_MEGA;
@@ -567,7 +586,7 @@ static pt_render_params resolve_auto(const pt_render_params *in) {
             // brute-force triangle scenes: a pixel that sees the mesh is a ~1.7 ms serial chain at 64 spp.  Small
             // frames are bounded by that tail -> scatter heavy pixels over warps (persistent + cooperative scan);
             // large frames have enough heavy tiles to fill the GPU, where the dense lane-serial scan is cheaper.
-            const long long pixels = (long long)p.width * (p.row_end > p.row_begin ? p.row_end - p.row_begin : p.height);
+            const long long pixels = (long long)p.width * nrows;     // the launch's own share, not the full frame
             p.kernel = pixels <= 400000 ? PT_KERNEL_PERSISTENT : PT_KERNEL_MEGA;
         }
     }
@@ -577,8 +596,9 @@ static pt_render_params resolve_auto(const pt_render_params *in) {
 }
 
 static int dispatch(pt_ctx c, const pt_render_params *pin, const pt::LaunchArgs &A) {
-    const pt_render_params resolved = resolve_auto(pin);
+    const pt_render_params resolved = resolve_auto(pin, A.nrows);
     const pt_render_params *p = &resolved;
+    DevLock lock(c->device);     // constant-scene bind + launch are one critical section per device
     PT_CUDA(cudaMemsetAsync(c->d_counters, 0, 8 * sizeof(unsigned long long), c->stream), "clear counters");
     if (A.nrows <= 0) return 0;
     if (p->variant == PT_VARIANT_BIDIR) {
@@ -620,7 +640,9 @@ extern "C" pt_event pt_launch_pathtracer(pt_ctx c, const pt_camera *cam, const p
     if (dispatch(c, p, A)) { pt_release_event(e); return nullptr; }
     cudaEventRecord(e->stop, c->stream);
     c->last_w = p->width; c->last_h = p->height; c->last_variant = p->variant;
-    c->last_rng_items = nitems;
+    // what pt_read_accum / pt_read_rng_state may copy: only what THIS launch wrote
+    c->accum_valid_w = p->want_accum ? p->width : 0; c->accum_valid_h = p->want_accum ? p->height : 0;
+    c->rng_valid_items = p->want_rng ? nitems : 0;
     return e;
 }
 
@@ -657,6 +679,7 @@ extern "C" pt_event pt_launch_lighttracer(pt_ctx c, int n_vlp_per_light, const u
     pt_event e = event_new(c);
     if (!e) return nullptr;
     cudaEventRecord(e->start, c->stream);
+    DevLock lock(c->device);
     if (pt_launch_light_tracer_kernels(c, ar, LA, n_vlp_per_light, c->d_vpls, nullptr, c->d_vpl_active, c->d_vpl_count)) {
         pt_release_event(e);
         return nullptr;
@@ -725,8 +748,9 @@ extern "C" void *pt_map_render(pt_ctx c, pt_event *evt) {
 }
 
 extern "C" int pt_read_accum(pt_ctx c, float *dst, size_t nfloats) {
-    if (!c->d_accum) return pt_fail(1, "pt_read_accum: last launch did not set want_accum");
-    size_t have = (size_t)c->last_w * c->last_h * 4;
+    if (!c || !c->d_accum || c->accum_valid_w <= 0) return pt_fail(1, "pt_read_accum: last launch did not set want_accum");
+    PT_CUDA(cudaSetDevice(c->device), "select device");
+    size_t have = (size_t)c->accum_valid_w * c->accum_valid_h * 4;
     if (nfloats < have) return pt_fail(1, "pt_read_accum: buffer too small");
     PT_CUDA(cudaMemcpyAsync(dst, c->d_accum, have * 4, cudaMemcpyDeviceToHost, c->stream), "read accum");
     PT_CUDA(cudaStreamSynchronize(c->stream), "sync");
@@ -734,8 +758,9 @@ extern "C" int pt_read_accum(pt_ctx c, float *dst, size_t nfloats) {
 }
 
 extern "C" int pt_read_rng_state(pt_ctx c, uint32_t *dst, size_t nwords) {
-    if (!c->d_rng) return pt_fail(1, "pt_read_rng_state: last launch did not set want_rng");
-    size_t have = c->last_rng_items * 4;
+    if (!c || !c->d_rng || c->rng_valid_items == 0) return pt_fail(1, "pt_read_rng_state: last launch did not set want_rng");
+    PT_CUDA(cudaSetDevice(c->device), "select device");
+    size_t have = c->rng_valid_items * 4;
     if (nwords < have) return pt_fail(1, "pt_read_rng_state: buffer too small");
     PT_CUDA(cudaMemcpyAsync(dst, c->d_rng, have * 4, cudaMemcpyDeviceToHost, c->stream), "read rng");
     PT_CUDA(cudaStreamSynchronize(c->stream), "sync");
@@ -807,6 +832,7 @@ extern "C" int pt_probe_trace(pt_ctx c, int variant, int arith, int n, const flo
     if (variant == PT_VARIANT_GRID && !c->grid_set) return pt_fail(1, "pt_probe_trace: no grid");
     PT_CUDA(cudaSetDevice(c->device), "select device");
     const int ar = arith != PT_ARITH_SEPARATE ? PT_ARITH_FMA : PT_ARITH_SEPARATE;
+    DevLock lock(c->device);
     int rc = pt_bind_const_scene(c, ar);
     if (rc) return rc;
     float *d_o, *d_d, *d_t, *d_n;
@@ -861,6 +887,78 @@ extern "C" int pt_probe_rng(pt_ctx c, const uint32_t seeds[4], uint32_t gid, int
     cudaMemcpyAsync(out_state, d_s, 16, cudaMemcpyDeviceToHost, c->stream);
     PT_CUDA(cudaStreamSynchronize(c->stream), "sync probe");
     cudaFree(d_f); cudaFree(d_s);
+    return 0;
+}
+
+// ---- measured peaks of THIS device for the roofline the benchmark reports (FP32 pipe and issue slots) ----
+namespace pt {
+// 8 independent FFMA chains per thread, 512 FFMAs per loop trip: the loop overhead is < 1 % of the instructions
+__global__ void __launch_bounds__(256) k_peak_ffma(float *out, int trips, float a, float b) {
+    float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+    for (int t = 0; t < trips; ++t) {
+#pragma unroll
+        for (int k = 0; k < 64; ++k) {
+            x0 = __fmaf_rn(x0, a, b); x1 = __fmaf_rn(x1, a, b); x2 = __fmaf_rn(x2, a, b); x3 = __fmaf_rn(x3, a, b);
+            x4 = __fmaf_rn(x4, a, b); x5 = __fmaf_rn(x5, a, b); x6 = __fmaf_rn(x6, a, b); x7 = __fmaf_rn(x7, a, b);
+        }
+    }
+    const float r = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (r == 123.456f) out[0] = r;                 // never true: keeps the chains alive
+}
+// the instruction mix of the tracers' inner loops in miniature: FP32 (FMA pipe), integer add / logic (ALU pipe) and
+// 32-bit integer multiply-add (the RNG), all independent — measures how many warp instructions per second the
+// schedulers really issue when no pipe is the limit by itself
+__global__ void __launch_bounds__(256) k_peak_issue(unsigned *out, int trips, float a, float b, unsigned m) {
+    float f0 = threadIdx.x * 1e-3f, f1 = f0 + 1.f, f2 = f0 + 2.f, f3 = f0 + 3.f;
+    unsigned i0 = threadIdx.x, i1 = i0 + 1u, i2 = i0 + 2u, i3 = i0 + 3u;
+    for (int t = 0; t < trips; ++t) {
+#pragma unroll
+        for (int k = 0; k < 64; ++k) {
+            f0 = __fmaf_rn(f0, a, b); i0 = (i0 ^ m) + i1;
+            f1 = __fmaf_rn(f1, a, b); i1 = (i1 + m) ^ i2;
+            f2 = __fmaf_rn(f2, a, b); i2 = (i2 ^ m) + i3;
+            f3 = __fmaf_rn(f3, a, b); i3 = (i3 + m) ^ i0;
+        }
+    }
+    const float r = (f0 + f1) + (f2 + f3);
+    const unsigned q = (i0 ^ i1) + (i2 ^ i3);
+    if (r == 123.456f && q == 77u) out[0] = q;
+}
+}  // namespace pt
+
+// out[0] = measured FP32 TFLOP/s (FFMA = 2 flop), out[1] = FFMA warp instructions per second (G),
+// out[2] = warp instructions per second of the mixed FP32 + integer kernel (G), out[3] = its duration in ms
+extern "C" int pt_measure_peaks(pt_ctx c, double out[4]) {
+    if (!c || !out) return pt_fail(1, "pt_measure_peaks: null argument");
+    PT_CUDA(cudaSetDevice(c->device), "select device");
+    float *d = nullptr;
+    PT_CUDA(cudaMalloc(&d, 64), "alloc");
+    cudaEvent_t e0, e1;
+    PT_CUDA(cudaEventCreate(&e0), "event"); PT_CUDA(cudaEventCreate(&e1), "event");
+    const int blocks = c->sm_count * 8, threads = 256, trips = 256;
+    float best_f = 1e30f, best_i = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {              // rep 0 warms the clocks up
+        cudaEventRecord(e0, c->stream);
+        pt::k_peak_ffma<<<blocks, threads, 0, c->stream>>>(d, trips, 1.0000001f, 1e-7f);
+        cudaEventRecord(e1, c->stream);
+        PT_CUDA(cudaEventSynchronize(e1), "peak kernel");
+        float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+        if (rep && ms < best_f) best_f = ms;
+        cudaEventRecord(e0, c->stream);
+        pt::k_peak_issue<<<blocks, threads, 0, c->stream>>>((unsigned *)d, trips, 1.0000001f, 1e-7f, 0x9E3779B9u);
+        cudaEventRecord(e1, c->stream);
+        PT_CUDA(cudaEventSynchronize(e1), "peak kernel");
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep && ms < best_i) best_i = ms;
+    }
+    PT_CUDA(cudaGetLastError(), "peak kernels");
+    const double threads_total = (double)blocks * threads, warps = threads_total / 32.0;
+    const double ffma_per_thread = (double)trips * 64 * 8;
+    out[0] = threads_total * ffma_per_thread * 2.0 / (best_f * 1e-3) / 1e12;
+    out[1] = warps * ffma_per_thread / (best_f * 1e-3) / 1e9;
+    out[2] = warps * ((double)trips * 64 * 12) / (best_i * 1e-3) / 1e9;     // 4 FFMA + 4 x (LOP3 + IADD) per inner step
+    out[3] = best_i;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
     return 0;
 }
 
@@ -935,20 +1033,27 @@ static int nccl_load(pt_nccl_api *a) {
     return 0;
 }
 
+extern "C" void pt_multi_destroy(pt_multi m);
+
 extern "C" pt_multi pt_multi_create(int ngpus) {
     if (ngpus < 1 || ngpus > 16 || ngpus > pt_device_count()) { pt_fail(1, "pt_multi_create: %d GPUs requested, %d visible", ngpus, pt_device_count()); return nullptr; }
     pt_multi m = (pt_multi)calloc(1, sizeof(pt_multi_s));
     m->n = ngpus;
     for (int i = 0; i < ngpus; ++i) {
         m->ctx[i] = pt_create(i);
-        if (!m->ctx[i]) return nullptr;
+        if (!m->ctx[i]) { pt_multi_destroy(m); return nullptr; }       // releases the contexts created so far
     }
     if (ngpus > 1) {
-        if (nccl_load(&m->nccl)) return nullptr;
+        if (nccl_load(&m->nccl)) { pt_multi_destroy(m); return nullptr; }
         int devs[16];
         for (int i = 0; i < ngpus; ++i) devs[i] = i;
         int rc = m->nccl.CommInitAll(m->comms, ngpus, devs);
-        if (rc) { pt_fail(rc, "ncclCommInitAll: %s", m->nccl.GetErrorString ? m->nccl.GetErrorString(rc) : "?"); return nullptr; }
+        if (rc) {
+            for (int i = 0; i < ngpus; ++i) m->comms[i] = nullptr;
+            pt_fail(rc, "ncclCommInitAll: %s", m->nccl.GetErrorString ? m->nccl.GetErrorString(rc) : "?");
+            pt_multi_destroy(m);
+            return nullptr;
+        }
     }
     return m;
 }
@@ -957,10 +1062,10 @@ extern "C" void pt_multi_destroy(pt_multi m) {
     if (!m) return;
     for (int i = 0; i < m->n; ++i) {
         cudaSetDevice(i);
-        if (m->n > 1 && m->comms[i]) m->nccl.CommDestroy(m->comms[i]);
+        if (m->n > 1 && m->comms[i] && m->nccl.CommDestroy) m->nccl.CommDestroy(m->comms[i]);
         cudaFree(m->accum[i]);
         cudaFree(m->rgba_scratch[i]);
-        pt_destroy(m->ctx[i]);
+        pt_destroy(m->ctx[i]);          // NULL-safe
     }
     free(m);
 }
@@ -995,49 +1100,69 @@ extern "C" pt_event pt_multi_launch_lighttracer(pt_multi m, int n_vlp_per_light,
 }
 
 extern "C" pt_event pt_multi_launch_pathtracer(pt_multi m, const pt_camera *cam, const pt_render_params *params) {
+    if (!m || !cam || !params) { pt_fail(1, "pt_multi_launch_pathtracer: null argument"); return nullptr; }
     if (m->n == 1) {
         pt_render_params p1 = *params;
         p1.sample_blocks = 0;
         return pt_launch_pathtracer(m->ctx[0], cam, &p1);
+    }
+    // ---- everything that can be rejected is rejected BEFORE any event or NCCL group exists
+    // sample_blocks > 1 asks for sample-range sharding instead of tiles: device i renders sample block i of the WHOLE image
+    const bool by_samples = params->sample_blocks > 1;
+    if (by_samples && params->sample_blocks != m->n) { pt_fail(1, "pt_multi: sample_blocks (%d) must equal the number of GPUs (%d)", params->sample_blocks, m->n); return nullptr; }
+    pt_render_params dev_params[16];
+    for (int i = 0; i < m->n; ++i) {
+        pt_render_params &p = dev_params[i];
+        p = *params;
+        if (by_samples) { p.sample_block = i; p.row_interleave = 0; p.rank = 0; p.nranks = 1; }
+        else { p.row_interleave = 8; p.rank = i; p.nranks = m->n; p.sample_block = 0; p.sample_blocks = 0; }
+        if (validate_params(m->ctx[i], &p)) return nullptr;
     }
     const size_t npix = (size_t)params->width * params->height;
     for (int i = 0; i < m->n; ++i) {
         PT_CUDA_NULL(cudaSetDevice(i), "select device");
         if (m->cap_pixels < npix) {
             cudaFree(m->accum[i]); cudaFree(m->rgba_scratch[i]);
+            m->accum[i] = nullptr; m->rgba_scratch[i] = nullptr;
+            m->cap_pixels = 0;                 // a failure below must not leave a stale capacity behind
             PT_CUDA_NULL(cudaMalloc(&m->accum[i], npix * 16), "alloc accumulation buffer");
             PT_CUDA_NULL(cudaMalloc(&m->rgba_scratch[i], npix * 4), "alloc scratch image");
         }
     }
-    m->cap_pixels = m->cap_pixels < npix ? npix : m->cap_pixels;
+    // (cap_pixels is per multi-context: all devices were (re)allocated together above)
+    if (m->cap_pixels < npix) m->cap_pixels = npix;
     pt_ctx c0 = m->ctx[0];
     PT_CUDA_NULL(cudaSetDevice(0), "select device");
     if (ensure_dev((void **)&c0->d_rgba, &c0->rgba_cap, npix * 4)) return nullptr;
     pt_event e = event_new(c0);
     if (!e) return nullptr;
+    bool group_open = false;
+    int rc = 0;
     cudaEventRecord(e->start, c0->stream);
-    // sample_blocks > 1 asks for sample-range sharding instead of tiles: device i renders sample block i of the WHOLE image
-    const bool by_samples = params->sample_blocks > 1;
-    if (by_samples && params->sample_blocks != m->n) { pt_fail(1, "pt_multi: sample_blocks (%d) must equal the number of GPUs (%d)", params->sample_blocks, m->n); return nullptr; }
-    for (int i = 0; i < m->n; ++i) {
-        PT_CUDA_NULL(cudaSetDevice(i), "select device");
-        pt_render_params p = *params;
-        if (by_samples) { p.sample_block = i; p.row_interleave = 0; p.rank = 0; p.nranks = 1; }
-        else { p.row_interleave = 8; p.rank = i; p.nranks = m->n; }
-        PT_CUDA_NULL(cudaMemsetAsync(m->accum[i], 0, npix * 16, m->ctx[i]->stream), "clear accumulation buffer");
-        if (pt_render_device(m->ctx[i], cam, &p, m->rgba_scratch[i], m->accum[i])) return nullptr;
+    for (int i = 0; i < m->n && !rc; ++i) {
+        if (cudaSetDevice(i) != cudaSuccess) { rc = pt_fail(1, "select device"); break; }
+        if (cudaMemsetAsync(m->accum[i], 0, npix * 16, m->ctx[i]->stream) != cudaSuccess) { rc = pt_fail(1, "clear accumulation buffer"); break; }
+        rc = pt_render_device(m->ctx[i], cam, &dev_params[i], m->rgba_scratch[i], m->accum[i]);
     }
-    // the only collective: sum the accumulation buffers onto device 0 (rows a device does not own are zero)
-    m->nccl.GroupStart();
-    for (int i = 0; i < m->n; ++i) {
-        int rc = m->nccl.Reduce(m->accum[i], m->accum[i], npix * 4, PT_NCCL_FLOAT32, PT_NCCL_SUM, 0, m->comms[i], m->ctx[i]->stream);
-        if (rc) { pt_fail(rc, "ncclReduce failed"); return nullptr; }
+    if (!rc) {
+        // the only collective: sum the accumulation buffers onto device 0 (rows a device does not own are zero)
+        m->nccl.GroupStart();
+        group_open = true;
+        for (int i = 0; i < m->n && !rc; ++i) {
+            int nrc = m->nccl.Reduce(m->accum[i], m->accum[i], npix * 4, PT_NCCL_FLOAT32, PT_NCCL_SUM, 0, m->comms[i], m->ctx[i]->stream);
+            if (nrc) rc = pt_fail(nrc, "ncclReduce failed: %s", m->nccl.GetErrorString ? m->nccl.GetErrorString(nrc) : "?");
+        }
     }
-    m->nccl.GroupEnd();
-    PT_CUDA_NULL(cudaSetDevice(0), "select device");
-    if (pt_tonemap_device(c0, m->accum[0], c0->d_rgba, params->width, params->height)) return nullptr;
+    if (group_open) {                              // never leave the NCCL group open, whatever happened inside it
+        int nrc = m->nccl.GroupEnd();
+        if (nrc && !rc) rc = pt_fail(nrc, "ncclGroupEnd failed: %s", m->nccl.GetErrorString ? m->nccl.GetErrorString(nrc) : "?");
+    }
+    if (!rc && cudaSetDevice(0) != cudaSuccess) rc = pt_fail(1, "select device");
+    if (!rc) rc = pt_tonemap_device(c0, m->accum[0], c0->d_rgba, params->width, params->height);
+    if (rc) { pt_release_event(e); return nullptr; }
     cudaEventRecord(e->stop, c0->stream);
     c0->last_w = params->width; c0->last_h = params->height; c0->last_variant = params->variant;
+    c0->accum_valid_w = c0->accum_valid_h = 0; c0->rng_valid_items = 0;
     m->last_w = params->width; m->last_h = params->height;
     return e;
 }

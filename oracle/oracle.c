@@ -428,6 +428,10 @@ static inline void cnt_add(oracle_counters *a, const oracle_counters *b) {
     a->tri_tests += b->tri_tests; a->cells_visited += b->cells_visited; a->prim_tests += b->prim_tests;
 }
 
+static int g_threads_used = 0;
+/* OpenMP team size of the most recent oracle_render (bench.py asserts the CPU baseline really ran on the cores it states) */
+int oracle_threads_used(void) { return g_threads_used; }
+
 int oracle_render(const oracle_job *J, uint8_t *rgba8, float *accum, uint32_t *rng_state, oracle_counters *counters) {
     if (!J || J->width <= 0 || J->height <= 0 || J->spp <= 0 || J->variant < 0 || J->variant > 4) return -1;
     if (J->variant == ORACLE_BIDIR && (J->nvpl < 0 || (J->nvpl > 0 && !J->vpls))) return -1;
@@ -457,7 +461,10 @@ int oracle_render(const oracle_job *J, uint8_t *rgba8, float *accum, uint32_t *r
         oracle_counters cnt;
         memset(&cnt, 0, sizeof(cnt));
 #ifdef _OPENMP
+        if (omp_get_thread_num() == 0) g_threads_used = omp_get_num_threads();
 #pragma omp for schedule(dynamic, 64)
+#else
+        g_threads_used = 1;
 #endif
         for (long lin = (long)r0 * W; lin < (long)r1 * W; ++lin) {
             {

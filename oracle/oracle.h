@@ -82,6 +82,8 @@ typedef struct {
  * 0,1,3; 64*W*H in the 8W x 8H work-item order for nodof).  Returns 0, or -1 on bad arguments. */
 int oracle_render(const oracle_job *job, uint8_t *rgba8, float *accum, uint32_t *rng_state,
                   oracle_counters *counters);
+/* OpenMP team size the most recent oracle_render really ran with (1 without OpenMP) */
+int oracle_threads_used(void);
 
 /* Kernel lightTracer of CLSuperBidirectionalPathTracer/bidirectionalpathtracer.ocl:280-326 for a 1-D range of
  * n_vlp_per_light work-items (scene, lights and seeds from `job`; its variant/size fields are ignored).

@@ -67,6 +67,7 @@ class OracleLib:
         L.oracle_light_tracer.restype = C.c_int
         L.oracle_light_tracer.argtypes = [C.POINTER(oracle_job), C.c_int, C.c_void_p, C.c_void_p, C.POINTER(oracle_counters)]
         L.oracle_contract_mode.restype = C.c_int
+        L.oracle_threads_used.restype = C.c_int
         L.oracle_randomize_id.restype = C.c_uint32
         L.oracle_randomize_id.argtypes = [C.c_uint32]
         L.oracle_build_grid.restype = C.c_uint64
@@ -229,7 +230,7 @@ class OracleLib:
         if rc:
             raise ValueError("oracle_render rejected the job")
         del keep
-        out = {"image": img, "accum": acc, "rng_state": rng, "counters": cnt.as_dict()}
+        out = {"image": img, "accum": acc, "rng_state": rng, "counters": cnt.as_dict(), "threads": int(self.lib.oracle_threads_used())}
         if variant == "bidir":
             out["vpls"] = vpls
         return out

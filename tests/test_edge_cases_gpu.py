@@ -149,3 +149,53 @@ def test_config5_frame_size_tiling_and_flavour_properties(renderer):
     other = renderer.render("grid", W, H, (1, 2, 3, 4), spp=spp, kernel="persistent", want_accum=True, want_rng=True)
     assert np.array_equal(other.accum.view(np.uint32), whole.accum.view(np.uint32))
     assert np.array_equal(other.rng_state, whole.rng_state)
+
+
+def test_grid_read_right_after_build_is_stream_ordered(oracle_fma):
+    """C-level sequence pt_build_grid -> pt_read_grid_csr with NO event wait in between: the build leaves its last kernels
+    unsynchronised on the context's non-blocking stream, so the reader itself has to order behind them."""
+    import ctypes as C
+    import gen_mesh
+    from opencl_montecarlo_path_tracing_b200 import _lib
+    lib = _lib.cuda_lib()
+    tris = gen_mesh.soup(200000, seed=5, box_size=36.0)
+    lo, hi = gen_mesh.bbox_like_reference(tris)
+    scene = pt.Scene(np.array(DEFAULT_SPH, np.int32), np.array(DEFAULT_SQ, np.int32), tris, np.array(LIGHTS2, np.float32), lo, hi)
+    g = pt.grid_dims(scene)
+    ncells = g.res[0] * g.res[1] * g.res[2]
+    ostart, orefs = oracle_fma.build_grid(tris, lo, np.array(g.res[:]), np.array(g.cell_size[:], np.float32))
+    ctx = lib.pt_create(0)
+    try:
+        cs = scene.to_c()
+        assert lib.pt_set_scene(ctx, C.byref(cs)) == 0
+        for _ in range(3):
+            evt = lib.pt_build_grid(ctx, C.byref(g))
+            assert evt
+            total = C.c_uint64()
+            start = np.full(ncells + 1, 0xFFFFFFFF, np.uint32)
+            assert lib.pt_read_grid_csr(ctx, start.ctypes.data_as(C.POINTER(C.c_uint32)), None, C.byref(total)) == 0
+            refs = np.full(int(total.value), 0xFFFFFFFF, np.uint32)
+            assert lib.pt_read_grid_csr(ctx, None, refs.ctypes.data_as(C.POINTER(C.c_uint32)), None) == 0
+            lib.pt_release_event(evt)
+            assert np.array_equal(start, ostart) and np.array_equal(refs, orefs)
+    finally:
+        lib.pt_destroy(ctx)
+
+
+def test_optional_buffers_are_only_readable_after_a_launch_that_wrote_them(renderer):
+    """pt_read_accum / pt_read_rng_state size their copies from the launch that actually produced the buffers: after a
+    bigger launch WITHOUT want_accum / want_rng they fail cleanly instead of reading past a small old allocation."""
+    import ctypes as C
+    scene, _ = _scene(DEFAULT_SPH, DEFAULT_SQ, ONE_TRI, LIGHTS2)
+    renderer.set_scene(scene)
+    small = renderer.render("lmem", 64, 64, SEED_SETS[0], want_accum=True, want_rng=True)
+    assert small.accum.shape == (64, 64, 4) and small.rng_state.shape == (64 * 64, 4)
+    renderer.render("lmem", 1024, 1024, SEED_SETS[0], spp=1)                      # neither buffer requested
+    lib = renderer._l
+    buf = np.zeros(1024 * 1024 * 4, np.float32)
+    assert lib.pt_read_accum(renderer.ctx, buf.ctypes.data_as(C.POINTER(C.c_float)), buf.size) != 0
+    assert b"want_accum" in lib.pt_last_error()
+    words = np.zeros(1024 * 1024 * 4, np.uint32)
+    assert lib.pt_read_rng_state(renderer.ctx, words.ctypes.data_as(C.POINTER(C.c_uint32)), words.size) != 0
+    again = renderer.render("lmem", 64, 64, SEED_SETS[0], want_accum=True, want_rng=True)
+    assert np.array_equal(again.accum.view(np.uint32), small.accum.view(np.uint32))
