@@ -13,17 +13,44 @@ BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
 
 
 def test_reference_arm_prints_one_contract_line():
-    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
-                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    # torchrun exports OMP_NUM_THREADS=1 to its children: the CPU arm must still use (and verify) every host core
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--cpu-budget", "2"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert p.returncode == 0, p.stderr[-2000:]
     lines = [l for l in p.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
     j = json.loads(lines[0])
     assert BASE_KEYS <= set(j) and j["impl"] == "reference" and j["vs_baseline"] is None
     assert j["metric"] == "Mrays/s" and j["unit"] == "Mrays/s" and j["higher_is_better"] is True and j["value"] > 0
-    assert j["config"]["workload"] == "nodof_512x512x64"
-    assert j["cpu_baseline"]["kind"] in ("reference", "port") and j["cpu_baseline"]["cores"] >= 1 and j["cpu_baseline"]["value"] == j["value"]
+    assert j["config"]["workload"] == "gridsoup1m_1920x1080x256" and j["config"]["baseline_config"] == 4
+    cores = len(os.sched_getaffinity(0))
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] == cores and j["cpu_baseline"]["value"] == j["value"]
+    assert "%d OpenMP threads verified" % cores in j["cpu_baseline"]["sample"]
     assert j["e2e"] == {"value": j["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_at_n_gt_1_is_the_strong_scaled_config5_scene_on_all_cores():
+    """rank 0 of a torchrun launch (OMP_NUM_THREADS=1 exported): same workload at every N, every host core."""
+    env = dict(os.environ, RANK="0", WORLD_SIZE="4", LOCAL_RANK="0", OMP_NUM_THREADS="1")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "4", "--steps", "1", "--warmup", "0",
+                        "--cpu-budget", "2"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert p.returncode == 0, p.stderr[-2000:]
+    j = json.loads(p.stdout.strip())
+    assert j["config"]["workload"] == "gridsoup1m_3840x2160x64" and j["config"]["height"] == 2160 and j["scaling"] == "strong"
+    assert j["n_gpus"] == 4 and j["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+
+
+def test_reference_arm_light_workload_runs_the_unmodified_reference_binary():
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "bin", "nodof", "CLSuperPathTracer")):
+        import pytest
+        pytest.skip("oracle/_ref not built")
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--workload", "nodof_512x512x64"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert p.returncode == 0, p.stderr[-2000:]
+    j = json.loads(p.stdout.strip())
+    assert j["cpu_baseline"]["kind"] == "reference" and "%d OpenMP threads" % len(os.sched_getaffinity(0)) in j["cpu_baseline"]["sample"]
 
 
 def test_reference_arm_other_ranks_stay_silent():
