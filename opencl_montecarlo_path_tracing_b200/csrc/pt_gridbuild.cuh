@@ -29,9 +29,51 @@ PT_DEV void tri_cell_range(const float *t, const GridDev &G, int lo[3], int hi[3
     }
 }
 
-__global__ void k_grid_count(const float *__restrict__ tris, int ntri, GridDev G, uint32_t *__restrict__ count) {
+// Small sphere around a triangle: the circumscribed circle's centre, or — obtuse triangles — the midpoint of the longest
+// edge, in plain float (any centre is valid, only the tightness depends on it); the radius is the largest vertex
+// distance from that centre, rounded up and inflated by 1 % + 0.01 exactly like the brute-force mesh / cluster spheres
+// (ptcuda.cu pt_set_scene), which dwarfs the float rounding of the distances.  Degenerate or non-finite input ->
+// radius +inf: the filter then always passes and the exact test decides.  (FP64 would cost 30 ms per 1 M-triangle build.)
+PT_DEV float4 tri_bound_sphere(const float *t) {
+    const float ax = t[0], ay = t[1], az = t[2];
+    const float ux = t[4] - ax, uy = t[5] - ay, uz = t[6] - az;      // B - A
+    const float vx = t[8] - ax, vy = t[9] - ay, vz = t[10] - az;     // C - A
+    const float uu = ux * ux + uy * uy + uz * uz, vv = vx * vx + vy * vy + vz * vz, uv = ux * vx + uy * vy + uz * vz;
+    const float ww = uu + vv - 2.0f * uv;                             // |C - B|^2
+    float cx, cy, cz;
+    const float den = 2.0f * (uu * vv - uv * uv);                     // 2 |u x v|^2
+    if (uu + vv <= ww)      { cx = 0.5f * (ux + vx); cy = 0.5f * (uy + vy); cz = 0.5f * (uz + vz); }   // angle at A >= 90: edge BC
+    else if (uu + ww <= vv) { cx = 0.5f * vx; cy = 0.5f * vy; cz = 0.5f * vz; }                        // angle at B >= 90: edge AC
+    else if (vv + ww <= uu) { cx = 0.5f * ux; cy = 0.5f * uy; cz = 0.5f * uz; }                        // angle at C >= 90: edge AB
+    else if (den > 1e-12f * (uu * vv)) {
+        const float s = vv * (uu - uv) / den, q = uu * (vv - uv) / den;   // circumcentre = A + s u + q v
+        cx = s * ux + q * vx; cy = s * uy + q * vy; cz = s * uz + q * vz;
+    } else                  { cx = (ux + vx) * (1.0f / 3.0f); cy = (uy + vy) * (1.0f / 3.0f); cz = (uz + vz) * (1.0f / 3.0f); }
+    const float fx = ax + cx, fy = ay + cy, fz = az + cz;
+    float r2 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float dx = t[4 * k] - fx, dy = t[4 * k + 1] - fy, dz = t[4 * k + 2] - fz;
+        r2 = fmaxf(r2, dx * dx + dy * dy + dz * dz);
+    }
+    const float rr = __fadd_ru(__fmul_ru(__fsqrt_ru(__fmul_ru(r2, 1.00001f)), 1.01f), 0.01f);
+    if (!(rr < 1e30f) || !(fabsf(fx) < 1e30f) || !(fabsf(fy) < 1e30f) || !(fabsf(fz) < 1e30f))
+        return make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
+    return make_float4(fx, fy, fz, rr);
+}
+
+__global__ void k_grid_count(const float *__restrict__ tris, int ntri, GridDev G, uint32_t *__restrict__ count, uint32_t *__restrict__ kmax_bits) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ntri) return;
+    {
+        // max |e0||e2| over the mesh (rounded up), for the distance-proportional margin of the sphere filter; finite
+        // non-negative floats order like their bit patterns, NaN / inf patterns order above every finite one
+        const float *t = tris + 12 * (size_t)i;
+        const float ux = t[4] - t[0], uy = t[5] - t[1], uz = t[6] - t[2], vx = t[8] - t[0], vy = t[9] - t[1], vz = t[10] - t[2];
+        const float kk = __fmul_ru(__fsqrt_ru((ux * ux + uy * uy + uz * uz) * (vx * vx + vy * vy + vz * vz)), 1.00001f);
+        uint32_t bits = __float_as_uint(kk) & 0x7fffffffu;
+        if (bits > *(volatile uint32_t *)kmax_bits) atomicMax(kmax_bits, bits);
+    }
     int lo[3], hi[3];
     tri_cell_range(tris + 12 * (size_t)i, G, lo, hi);
     for (int z = lo[2]; z <= hi[2]; ++z)
@@ -141,7 +183,7 @@ __global__ void k_scan_add(uint32_t *__restrict__ out, size_t n, const uint32_t 
 __global__ void k_grid_emit(const float *__restrict__ tris, size_t ncells, uint32_t cap,
                             const uint32_t *__restrict__ raw_start, uint32_t *__restrict__ raw_refs,
                             const uint32_t *__restrict__ cap_start, uint32_t *__restrict__ refs,
-                            float4 *__restrict__ recs, uint2 *__restrict__ cells) {
+                            float4 *__restrict__ recs, float4 *__restrict__ sph, uint2 *__restrict__ cells) {
     size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncells) return;
     uint32_t b = raw_start[c], e = raw_start[c + 1];
@@ -165,6 +207,7 @@ __global__ void k_grid_emit(const float *__restrict__ tris, size_t ncells, uint3
         r[0] = make_float4(e2x, e2y, e2z, e0x);
         r[1] = make_float4(e0y, e0z, t[0], t[1]);
         r[2] = make_float4(t[2], __uint_as_float(id), 0.f, 0.f);
+        sph[first + k] = tri_bound_sphere(t);
     }
 }
 
@@ -188,7 +231,7 @@ int pt_grid_build_device(pt_ctx ctx, const pt_grid *g) {
     for (int a = 0; a < 3; ++a) {
         G.bmin[a] = g->box_min[a]; G.bmax[a] = g->box_max[a]; G.cell[a] = g->cell_size[a]; G.res[a] = g->res[a];
     }
-    G.cells = nullptr; G.recs = nullptr;
+    G.cells = nullptr; G.recs = nullptr; G.sph = nullptr; G.sph_k = INFINITY;
 
     // All buffers of the build live in the context and only ever grow: cudaMalloc / cudaFree of the ~250 MB a 1 M-
     // triangle grid needs cost 80 ms per build, 300x the 0.24 ms the nine kernels take.
@@ -211,34 +254,45 @@ int pt_grid_build_device(pt_ctx ctx, const pt_grid *g) {
     uint32_t *d_count = ctx->gb_count, *d_raw_start = ctx->gb_raw_start, *d_cursor = ctx->gb_cursor, *d_bsums = ctx->gb_bsums;
     PT_CUDA(cudaMemsetAsync(d_count, 0, ncells * 4, ctx->stream), "memset");
     PT_CUDA(cudaMemsetAsync(d_cursor, 0, ncells * 4, ctx->stream), "memset");
+    if (grow((void **)&ctx->gb_kmax, &ctx->gb_cap[9], 4, "alloc kmax")) return 1;
+    PT_CUDA(cudaMemsetAsync(ctx->gb_kmax, 0, 4, ctx->stream), "memset");
 
     const int tb = 256, tg = (ntri + tb - 1) / tb;
-    uint32_t raw_total = 0, cap_total = 0;
+    uint32_t raw_total = 0, cap_total = 0, kmax_bits = 0;
     if (ntri > 0) {
-        k_grid_count<<<tg, tb, 0, ctx->stream>>>(ctx->d_tris_raw, ntri, G, d_count);
+        k_grid_count<<<tg, tb, 0, ctx->stream>>>(ctx->d_tris_raw, ntri, G, d_count, ctx->gb_kmax);
         PT_CUDA(cudaGetLastError(), "grid count");
     }
     if (exclusive_scan(ctx, d_count, ncells, 0, d_raw_start, d_bsums)) return 1;
     if (exclusive_scan(ctx, d_count, ncells, cap, ctx->d_cell_start, d_bsums)) return 1;
     PT_CUDA(cudaMemcpyAsync(&raw_total, d_raw_start + ncells, 4, cudaMemcpyDeviceToHost, ctx->stream), "read total");
     PT_CUDA(cudaMemcpyAsync(&cap_total, ctx->d_cell_start + ncells, 4, cudaMemcpyDeviceToHost, ctx->stream), "read total");
+    PT_CUDA(cudaMemcpyAsync(&kmax_bits, ctx->gb_kmax, 4, cudaMemcpyDeviceToHost, ctx->stream), "read kmax");
     PT_CUDA(cudaStreamSynchronize(ctx->stream), "sync grid totals");
     if (grow((void **)&ctx->gb_raw_refs, &ctx->gb_cap[6], (size_t)(raw_total ? raw_total : 1) * 4, "alloc raw refs")) return 1;
     if (grow((void **)&ctx->d_refs, &ctx->gb_cap[7], (size_t)(cap_total ? cap_total : 1) * 4, "alloc refs")) return 1;
     if (grow((void **)&ctx->d_recs, &ctx->gb_cap[8], (size_t)(cap_total ? cap_total : 1) * 3 * sizeof(float4), "alloc records")) return 1;
+    if (grow((void **)&ctx->d_sph, &ctx->gb_cap[10], (size_t)(cap_total ? cap_total : 1) * sizeof(float4), "alloc record spheres")) return 1;
     uint32_t *d_raw_refs = ctx->gb_raw_refs;
     if (ntri > 0) {
         k_grid_fill<<<tg, tb, 0, ctx->stream>>>(ctx->d_tris_raw, ntri, G, d_raw_start, d_cursor, d_raw_refs);
         PT_CUDA(cudaGetLastError(), "grid fill");
     }
     k_grid_emit<<<(unsigned)((ncells + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_tris_raw, ncells, cap, d_raw_start, d_raw_refs,
-                                                                        ctx->d_cell_start, ctx->d_refs, ctx->d_recs,
+                                                                        ctx->d_cell_start, ctx->d_refs, ctx->d_recs, ctx->d_sph,
                                                                         ctx->d_cells);
     PT_CUDA(cudaGetLastError(), "grid emit");
     // no synchronisation here: the render that follows is ordered behind the build on the same stream
 
     G.cells = ctx->d_cells;
     G.recs = ctx->d_recs;
+    G.sph = ctx->d_sph;
+    {
+        float kmax;
+        memcpy(&kmax, &kmax_bits, 4);
+        const double k = 2e-4 * (double)kmax + 1e-6;          // same margin law as the brute-force mesh cull (pt_set_scene)
+        G.sph_k = (kmax_bits < 0x7f800000u && k < 1e30) ? (float)k : INFINITY;
+    }
     ctx->grid = G;
     ctx->grid_desc = *g;
     ctx->ncells = ncells;

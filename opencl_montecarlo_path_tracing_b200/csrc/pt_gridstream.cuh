@@ -94,6 +94,7 @@ template <bool FMA>
 PT_DEV bool cursor_visit(const GridDev &G, V3 o, V3 d, float &t, int &hit, Cursor &C, Counters &cnt) {
     cnt.cells++;
     cnt.gtri += C.cell.y;
+    cnt.btests += C.cell.y;
     const float4 *rec = G.recs + 3 * (size_t)C.cell.x;
     for (uint32_t k = 0; k < C.cell.y; ++k, rec += 3) {
         float4 ra = __ldg(rec), rb = __ldg(rec + 1), rc = __ldg(rec + 2);

@@ -57,7 +57,7 @@ PT_DEV void coop_test(CoopStage &st, int s, uint2 cell, V3 o, V3 d, float &t, in
         if (ok != 0x7fffffff && (bestk == 0x7fffffff || ob < best || (ob == best && ok < bestk))) { best = ob; bestk = ok; }
     }
     if (bestk != 0x7fffffff) { t = best; hit = hit_make(HIT_TRI, (int)cell.x + bestk); }
-    if (lane == 0) { cnt.cells++; cnt.gtri += cell.y; }
+    if (lane == 0) { cnt.cells++; cnt.gtri += cell.y; cnt.btests += cell.y; }
     __syncwarp();
 }
 

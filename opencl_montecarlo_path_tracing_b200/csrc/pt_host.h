@@ -69,12 +69,14 @@ struct pt_ctx_s {
     pt::GridDev grid;
     uint2 *d_cells;
     float4 *d_recs;
+    float4 *d_sph;                // per record: bounding sphere of its triangle (sphere prefilter of the traversal)
+    uint32_t *gb_kmax;            // bit pattern of max |e0||e2| over the mesh (grid build)
     uint32_t *d_refs;             // capped refs (triangle ids), CSR order
     uint32_t *d_cell_start;       // ncells + 1
     uint64_t total_refs;
     size_t ncells;
     uint32_t *gb_count, *gb_raw_start, *gb_cursor, *gb_bsums, *gb_raw_refs;   // build scratch, kept between builds
-    size_t gb_cap[9];             // capacities (bytes) of the five scratch buffers, cell_start, cells, refs, recs
+    size_t gb_cap[11];            // capacities (bytes) of the five scratch buffers, cell_start, cells, refs, recs
 
     // render targets owned by the context
     uint32_t *d_rgba;
@@ -130,6 +132,7 @@ int pt_launch_wavefront(pt_ctx ctx, const pt_render_params *p, const pt::LaunchA
 int pt_launch_grid_tma(pt_ctx ctx, const pt_render_params *p, const pt::LaunchArgs &args);
 int pt_grid_build_device(pt_ctx ctx, const pt_grid *g);
 int pt_launch_stream_grid(pt_ctx ctx, const pt_render_params *p, const pt::LaunchArgs &args);
+int pt_launch_grid_pool(pt_ctx ctx, const pt_render_params *p, const pt::LaunchArgs &args);
 int pt_launch_bidir(pt_ctx ctx, const pt_render_params *p, const pt::LaunchArgs &args);
 int pt_launch_light_tracer_kernels(pt_ctx ctx, int arith, const pt::LaunchArgs &args, int n, float4 *vpl, uint4 *rng_out,
                                    float4 *active, int *count);

@@ -70,7 +70,7 @@ PT_DEV void flush_counters(const LaunchArgs &P, const Counters &c, int ntri_coun
             case 3: v = g + r * (unsigned long long)ntri_counted; break;             // tri_tests (nominal)
             case 4: v = s_raw[3]; break;                                             // cells visited
             case 5: v = r * (unsigned long long)nprims; break;                       // prim_tests
-            default: v = g + (unsigned long long)s_raw[5]; break;                     // tri_tests executed (grid + brute force)
+            default: v = s_raw[5]; break;                                            // tri_tests executed (after the conservative culls)
         }
         if (v) atomicAdd(P.counters + threadIdx.x, v);
     }

@@ -22,6 +22,7 @@
 #include "pt_gridtma.cuh"
 #include "pt_bidir.cuh"
 #include "pt_gridstream.cuh"
+#include "pt_gridpool.cuh"
 
 // ------------------------------------------------------------------------------------ errors
 static std::atomic<int> g_error_mode{PT_ERRORS_EXIT};
@@ -142,7 +143,7 @@ extern "C" void pt_destroy(pt_ctx c) {
         cudaFree(c->d_scene[a]);
     }
     cudaFree(c->d_tris_raw);
-    cudaFree(c->d_cells); cudaFree(c->d_recs); cudaFree(c->d_refs); cudaFree(c->d_cell_start);
+    cudaFree(c->d_cells); cudaFree(c->d_recs); cudaFree(c->d_refs); cudaFree(c->d_cell_start); cudaFree(c->d_sph); cudaFree(c->gb_kmax);
     cudaFree(c->gb_count); cudaFree(c->gb_raw_start); cudaFree(c->gb_cursor); cudaFree(c->gb_bsums); cudaFree(c->gb_raw_refs);
     cudaFree(c->d_rgba); cudaFree(c->d_accum); cudaFree(c->d_rng); cudaFree(c->d_counters); cudaFree(c->d_scratch);
     cudaFree(c->d_vpls); cudaFree(c->d_vpl_active); cudaFree(c->d_vpl_count);
@@ -526,6 +527,7 @@ static int fill_args(pt_ctx c, const pt_camera *cam, const pt_render_params *p, 
     A->rgba = d_rgba; A->accum = d_accum; A->rng_out = d_rng;
     A->counters = c->d_counters;
     A->grid = c->grid;
+    if (p->no_cull) A->grid.sph_k = INFINITY;       // sphere prefilter of the grid traversal off: every record is tested
     const int arith = p->arith != PT_ARITH_SEPARATE ? PT_ARITH_FMA : PT_ARITH_SEPARATE;
     A->gscene = c->d_scene[arith];
     A->scene_bytes = p->variant == PT_VARIANT_GRID ? (int)offsetof(pt::SceneBlock, tri) : c->scene_bytes;  // grid: no brute-force records
@@ -611,6 +613,9 @@ static int dispatch(pt_ctx c, const pt_render_params *pin, const pt::LaunchArgs 
         case PT_KERNEL_GRID_STREAM:
             if (p->variant != PT_VARIANT_GRID) return pt_fail(1, "PT_KERNEL_GRID_STREAM applies to the trianglegrid variant only");
             return pt_launch_stream_grid(c, p, A);
+        case PT_KERNEL_GRID_POOL:
+            if (p->variant != PT_VARIANT_GRID) return pt_fail(1, "PT_KERNEL_GRID_POOL applies to the trianglegrid variant only");
+            return pt_launch_grid_pool(c, p, A);
         case PT_KERNEL_WAVEFRONT: return pt_launch_wavefront(c, p, A);
         case PT_KERNEL_GRID_TMA: return pt_launch_grid_tma(c, p, A);
     }

@@ -82,13 +82,13 @@ def test_soup1m_device_grid_equals_oracle_grid(soup_renderer, soup1m, oracle_fma
 
 
 @pytest.mark.parametrize("arith", ["fma", "separate"])
-@pytest.mark.parametrize("kernel", ["auto", "mega", "persistent"])
+@pytest.mark.parametrize("kernel", ["auto", "mega", "persistent", "grid_pool"])
 def test_config4_soup1m_1920x1080x256_windows(soup_renderer, soup1m, oracle_fma, oracle_sep, arith, kernel):
     r, g = soup_renderer
     o = oracle_fma if arith == "fma" else oracle_sep
     grid = _ogrid(o, soup1m[1], g)
     # windows of 4 rows spread over the frame: sky + box top, box interior, box + floor, floor at the bottom
-    windows = [(100, 104), (420, 424), (700, 704), (1072, 1076)] if kernel != "persistent" else [(420, 424), (1072, 1076)]
+    windows = [(100, 104), (420, 424), (700, 704), (1072, 1076)] if kernel not in ("persistent",) else [(420, 424), (1072, 1076)]
     for rows in windows:
         _check_window(r, o, soup1m[1], grid, 1920, 1080, 256, rows, "config 4 %s/%s rows %s" % (kernel, arith, rows), arith=arith, kernel=kernel)
 

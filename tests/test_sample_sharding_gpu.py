@@ -26,7 +26,7 @@ def _setup(renderer, scene_dirs, o, variant):
 
 
 @pytest.mark.parametrize("variant,kernels", [("base", ("mega", "persistent", "wavefront")), ("lmem", ("mega", "persistent")),
-                                             ("grid", ("mega", "persistent", "wavefront", "grid_tma", "grid_stream")),
+                                             ("grid", ("mega", "persistent", "wavefront", "grid_tma", "grid_stream", "grid_pool")),
                                              ("bidir", ("mega",))])
 def test_blocks_bit_exact_and_sum_to_the_frame(renderer, scene_dirs, oracle_fma, variant, kernels):
     osc, extra = _setup(renderer, scene_dirs, oracle_fma, variant)

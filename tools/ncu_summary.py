@@ -27,7 +27,10 @@ KEYS = [
     ("sm__sass_thread_inst_executed_op_ffma_pred_on.sum", "thread FFMA"), ("sm__sass_thread_inst_executed_op_fmul_pred_on.sum", "thread FMUL"),
     ("sm__sass_thread_inst_executed_op_fadd_pred_on.sum", "thread FADD"),
     ("smsp__sass_thread_inst_executed_op_fp32_pred_on.sum", "thread FP32 inst"),
-    ("lts__t_bytes.sum", "L2 bytes"), ("lts__t_sector_hit_rate.pct", "L2 hit %"),
+    ("lts__t_sectors.sum", "L2 sectors (x 32 B)"), ("lts__t_sectors.sum.per_second", "L2 sectors per second"),
+    ("lts__t_sectors.sum.pct_of_peak_sustained_elapsed", "L2 sector throughput % of peak"),
+    ("SM_B.TriageCompute.l1tex__t_sectors.sum", "L1 sectors (x 32 B)"),
+    ("lts__t_sector_hit_rate.pct", "L2 hit %"),
     ("l1tex__t_sector_hit_rate.pct", "L1 hit %"),
     ("dram__bytes_read.sum", "DRAM read"), ("dram__bytes_write.sum", "DRAM write"),
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM throughput %"),
@@ -47,6 +50,23 @@ def main():
             v = get(k)
             if v:
                 print("   %-40s %s %s" % (label, v[0], v[1]))
+        # achieved L2 / L1 bandwidth in GB/s (sectors are 32 B), the evidence behind "L2-resident, not HBM-bound"
+        def num(k):
+            v = get(k)
+            try:
+                return float(v[0].replace(",", "")), v[1]
+            except Exception:
+                return None, None
+        dur, du = num("gpu__time_duration.sum")
+        scale = {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0, "nsecond": 1e-9, "usecond": 1e-6, "msecond": 1e-3, "second": 1.0}.get(du or "", None)
+        l2s, _ = num("lts__t_sectors.sum")
+        l1s, _ = num("SM_B.TriageCompute.l1tex__t_sectors.sum")
+        dr, dru = num("dram__bytes_read.sum")
+        if dur and scale:
+            if l2s:
+                print("   %-40s %.1f GB/s" % ("L2 achieved bandwidth", l2s * 32 / (dur * scale) / 1e9))
+            if l1s:
+                print("   %-40s %.1f GB/s" % ("L1 achieved bandwidth (sectors)", l1s * 32 / (dur * scale) / 1e9))
         stalls = []
         for i, h in enumerate(hdr):
             if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio") or \

@@ -30,6 +30,6 @@ with pt.Renderer(0) as r:
             res = r.render("grid", W, H, (1, 2, 3, 4), spp=spp, kernel=kernel, read_image=False)
             best = min(best, res.ms)
         c = res.counters
-        print("grid soup n=%d %-10s %dx%d spp %d: %9.3f ms  %8.1f Mrays/s %8.1f Msamples/s  cells/ray %.2f tests/ray %.2f" % (
+        print("grid soup n=%d %-10s %dx%d spp %d: %9.3f ms  %8.1f Mrays/s %8.1f Msamples/s  cells/ray %.2f tests/ray %.2f exact/ray %.2f" % (
             n, kernel, W, H, spp, best, c["rays"] / 1e3 / best, c["samples"] / 1e3 / best, c["cells_visited"] / c["rays"],
-            c["tri_tests"] / c["rays"]), flush=True)
+            c["tri_tests"] / c["rays"], c["tri_tests_executed"] / c["rays"]), flush=True)
