@@ -27,6 +27,9 @@ struct LaunchArgs {
     const SceneBlock *gscene;      // global-memory copy of the scene block (shared-memory staging source)
     int scene_bytes;               // bytes of the block actually used (header + prims + ntri records)
     uint32_t scatter_mul;          // persistent kernel: work item w -> (w * scatter_mul) % nitems (0 = identity)
+    const uint32_t *tile_order;    // big-grid megakernel: CTA b renders tile tile_order[b] (heavy tiles first); NULL = identity
+    uint32_t tiles_x;              //   tiles per row of that launch
+    unsigned long long *cta_times; // diagnostics (PT_CTA_TIMES=1, big-grid megakernel): per CTA {start ns, end ns} of globaltimer
     const float4 *vpl;             // bidirectional variant: non-zero VPLs, dense, in buffer order
     const int *nvpl_active;        //   their number (device memory: written by k_compact_vpls)
 };
@@ -96,6 +99,13 @@ struct pt_ctx_s {
     float4 *d_vpls, *d_vpl_active;
     int *d_vpl_count;
     size_t vpls_cap;              // entries allocated
+
+    // launch order of the big-grid megakernel's tiles (heavy first), cached while the launch geometry stays the same
+    uint32_t *d_tile_order, *h_tile_order;
+    unsigned long long *d_cta_times, *h_cta_times;   // per CTA {start, end} of globaltimer (ns)
+    size_t tile_order_cap;
+    unsigned char tile_order_key[192];
+    int tile_order_state;         // 0 none, 1 sorted from the 1-spp pre-pass, 2 a full launch is recording, 3 sorted from a full launch
 
     // wavefront / persistent scratch
     void *d_scratch;

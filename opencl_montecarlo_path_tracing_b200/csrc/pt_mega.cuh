@@ -10,6 +10,10 @@
 //                 32), and five shuffle-down steps finish the reference's exact reduction tree in
 //                 registers — no scratch image, no second launch, same float sums.
 #pragma once
+#include <algorithm>
+#include <utility>
+#include <vector>
+
 #include "pt_host.h"
 
 namespace pt {
@@ -89,8 +93,17 @@ __global__ void __launch_bounds__(128, (BIG && VARIANT == PT_VARIANT_GRID) ? 8 :
     const SceneBlock *S = (MEM == PT_SCENE_SMEM) ? stage_scene_smem(P, smem_raw) : &c_scene;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int i = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-    const int vr = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    unsigned long long t_start = 0;
+    if (BIG && GRID && P.cta_times && threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start));
+    // tile of this CTA: its 2-D block index, or — 1-D launches of the big-grid kernel — entry blockIdx.x of the launch order
+    // (longest tile first, see launch_pixel_b)
+    uint32_t bx = blockIdx.x, by = blockIdx.y;
+    if (BIG && GRID && P.tile_order) {
+        const uint32_t tile = __ldg(P.tile_order + blockIdx.x);
+        by = tile / P.tiles_x; bx = tile - by * P.tiles_x;
+    }
+    const int i = bx * 16 + (warp & 1) * 8 + (lane & 7);
+    const int vr = by * 8 + (warp >> 1) * 4 + (lane >> 3);
     Counters cnt = {0, 0, 0, 0, 0, 0};
     const int j = map_row(P, vr);
     if (i < P.W && vr < P.nrows && j < P.row_end) {
@@ -111,6 +124,12 @@ __global__ void __launch_bounds__(128, (BIG && VARIANT == PT_VARIANT_GRID) ? 8 :
         if (P.rng_out) P.rng_out[pix] = make_uint4(rng.x0, rng.x1, rng.c0, rng.c1);
     }
     flush_counters(P, cnt, GRID ? 0 : S->ntri_counted, P.ap.nsq + P.ap.nsp);
+    if (BIG && GRID && P.cta_times && threadIdx.x == 0) {
+        unsigned long long t_end;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_end));
+        const size_t b = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+        P.cta_times[2 * b] = t_start; P.cta_times[2 * b + 1] = t_end;
+    }
 }
 
 template <bool FMA, int MEM>     // 8 warps = a 4x2 pixel tile per CTA (4x1 tiles time the same, 2x1 tiles 3 % slower)
@@ -157,15 +176,110 @@ __global__ void __launch_bounds__(256, 4) k_mega_nodof(const __grid_constant__ L
     flush_counters(P, cnt, S->ntri_counted, P.ap.nsq + P.ap.nsp);
 }
 
+// ---- launch order of the big-grid megakernel's tiles: LONGEST FIRST, from measured CTA durations -----------------------
+// A pixel's sample chain is indivisible, so the unit of work is one CTA (16x8 pixels) — 5.1 ms on average, up to 12.9 ms,
+// for one rank's stripes of the strong-scaled config-5 frame (3840x2160x64 over 8 ranks), whose whole launch is 6.9 waves
+// = 39 ms long.  In raster order the last CTAs start at 32.5 ms and the launch ramps down for another 8.5 ms: 85.6 % of
+// the CTA slot-time is used (98.3 % for the full frame on one GPU) — the 11 % the strong-scaling curve lost at N = 8
+// (tools/cta_timeline.py, profiles/r2_09).  The hardware hands out CTAs in block-index order, so the kernel reads its
+// tile from a table sorted by COST, longest first (LPT list scheduling): the cheap tiles fill the end of the launch.
+// Costs are measured, not guessed: the first launch of a geometry runs a 1-spp pre-pass (1/spp of the frame, its output
+// overwritten) in which every CTA records its globaltimer span; the first full launch records again and the table is
+// re-sorted from those exact durations for all later launches of the same geometry.  Which CTA renders which tile never
+// affects results.  (Classifying tiles by "primary ray hits the grid box" was tried first: no gain — floor tiles are as
+// expensive, their shadow rays cross the grid.  1-warp CTAs, to shrink the unit, lost 3 %.)
+struct TileOrderKey {
+    int W, H, row_begin, row_end, nrows, stripe_h, rank, nranks, variant_fma, ntri;
+    unsigned long long scene_version;
+    Camera cam;
+    float bmin[3], bmax[3], cell[3];
+    int res[3];
+};
+
+static int tile_order_rebuild(pt_ctx ctx, size_t n, bool identity) {
+    PT_CUDA(cudaMemcpyAsync(ctx->h_cta_times, ctx->d_cta_times, n * 16, cudaMemcpyDeviceToHost, ctx->stream), "read CTA times");
+    PT_CUDA(cudaStreamSynchronize(ctx->stream), "sync CTA times");
+    std::vector<std::pair<unsigned long long, uint32_t>> cost(n);
+    for (size_t b = 0; b < n; ++b) {
+        const unsigned long long t0 = ctx->h_cta_times[2 * b], t1 = ctx->h_cta_times[2 * b + 1];
+        const uint32_t tile = identity ? (uint32_t)b : ctx->h_tile_order[b];
+        cost[b] = std::make_pair(t1 > t0 ? t1 - t0 : 0ull, tile);
+    }
+    std::sort(cost.begin(), cost.end(), [](const std::pair<unsigned long long, uint32_t> &a, const std::pair<unsigned long long, uint32_t> &b) {
+        return a.first != b.first ? a.first > b.first : a.second < b.second;
+    });
+    for (size_t b = 0; b < n; ++b) ctx->h_tile_order[b] = cost[b].second;
+    PT_CUDA(cudaMemcpyAsync(ctx->d_tile_order, ctx->h_tile_order, n * 4, cudaMemcpyHostToDevice, ctx->stream), "upload tile order");
+    return 0;
+}
+
 template <int VARIANT, bool FMA, int MEM, bool BIG>
 static int launch_pixel_b(pt_ctx ctx, const LaunchArgs &args_in) {
     LaunchArgs args = args_in;
     args.ap.tri_coop = MEM == PT_SCENE_SMEM;
     dim3 grid((args.W + 15) / 16, (args.nrows + 7) / 8), block(128);
-    size_t smem = MEM == PT_SCENE_SMEM ? (size_t)args.scene_bytes : 0;
+    const size_t smem = MEM == PT_SCENE_SMEM ? (size_t)args.scene_bytes : 0;
     if (smem > 48 * 1024)
         PT_CUDA(cudaFuncSetAttribute(k_mega_pixel<VARIANT, FMA, MEM, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                 "opt-in shared memory");
+    if (BIG && VARIANT == PT_VARIANT_GRID) {
+        static int order = -1;
+        if (order == -1) { const char *e = getenv("PT_TILE_ORDER"); order = e ? atoi(e) : 1; }
+        const size_t n = (size_t)grid.x * grid.y;
+        // worth it when the launch is long (many samples) but only a few dozen waves short
+        if (order && args.spp >= 16 && n >= (size_t)ctx->sm_count * 16) {
+            TileOrderKey key;
+            memset(&key, 0, sizeof(key));
+            key.W = args.W; key.H = args.H; key.row_begin = args.row_begin; key.row_end = args.row_end; key.nrows = args.nrows;
+            key.stripe_h = args.stripe_h; key.rank = args.rank; key.nranks = args.nranks; key.variant_fma = VARIANT * 4 + (FMA ? 2 : 0) + MEM;
+            key.ntri = ctx->ntri_total; key.scene_version = ctx->scene_version; key.cam = args.cam;
+            for (int a = 0; a < 3; ++a) { key.bmin[a] = args.grid.bmin[a]; key.bmax[a] = args.grid.bmax[a]; key.cell[a] = args.grid.cell[a]; key.res[a] = args.grid.res[a]; }
+            static_assert(sizeof(TileOrderKey) <= sizeof(ctx->tile_order_key), "tile order key buffer too small");
+            if (ctx->tile_order_cap < n) {
+                PT_CUDA(cudaStreamSynchronize(ctx->stream), "sync before growing the tile order");
+                cudaFree(ctx->d_tile_order); cudaFree(ctx->d_cta_times);
+                if (ctx->h_tile_order) cudaFreeHost(ctx->h_tile_order);
+                if (ctx->h_cta_times) cudaFreeHost(ctx->h_cta_times);
+                ctx->d_tile_order = nullptr; ctx->h_tile_order = nullptr; ctx->d_cta_times = nullptr; ctx->h_cta_times = nullptr;
+                ctx->tile_order_cap = 0; ctx->tile_order_state = 0;
+                PT_CUDA(cudaMalloc(&ctx->d_tile_order, n * 4), "alloc tile order");
+                PT_CUDA(cudaMalloc(&ctx->d_cta_times, n * 16), "alloc CTA times");
+                PT_CUDA(cudaMallocHost(&ctx->h_tile_order, n * 4), "alloc pinned tile order");
+                PT_CUDA(cudaMallocHost(&ctx->h_cta_times, n * 16), "alloc pinned CTA times");
+                ctx->tile_order_cap = n;
+            }
+            const bool same = ctx->tile_order_state != 0 && memcmp(&key, ctx->tile_order_key, sizeof(key)) == 0;
+            if (!same) {
+                // state 0 -> 1: costs from a 1-spp pre-pass in raster order (image written here is overwritten below)
+                LaunchArgs pre = args;
+                pre.spp = 1; pre.accum = nullptr; pre.rng_out = nullptr; pre.tile_order = nullptr; pre.cta_times = ctx->d_cta_times;
+                k_mega_pixel<VARIANT, FMA, MEM, BIG><<<grid, block, smem, ctx->stream>>>(pre);
+                PT_CUDA(cudaGetLastError(), "launch k_mega_pixel (cost pre-pass)");
+                if (args.counters) PT_CUDA(cudaMemsetAsync(args.counters, 0, 8 * sizeof(unsigned long long), ctx->stream), "clear counters");
+                if (tile_order_rebuild(ctx, n, true)) return 1;
+                memcpy(ctx->tile_order_key, &key, sizeof(key));
+                ctx->tile_order_state = 1;
+            } else if (ctx->tile_order_state == 2) {
+                // state 2 -> 3: the previous full launch recorded its CTA spans: re-sort from those exact durations, once
+                if (tile_order_rebuild(ctx, n, false)) return 1;
+                ctx->tile_order_state = 3;
+            }
+            args.tile_order = ctx->d_tile_order;
+            args.tiles_x = grid.x;
+            if (ctx->tile_order_state == 1) { args.cta_times = ctx->d_cta_times; ctx->tile_order_state = 2; }
+            grid = dim3((unsigned)n, 1);
+        }
+        if (getenv("PT_CTA_TIMES")) {                 // diagnostics: pt_debug_read_scratch() returns the table (block-index order)
+            const size_t nb = (size_t)grid.x * grid.y;
+            if (pt_ensure_scratch(ctx, nb * 16 + 256)) return 1;
+            unsigned long long *diag = (unsigned long long *)((char *)ctx->d_scratch + 256);
+            if (!args.cta_times) { args.cta_times = diag; diag = nullptr; }
+            k_mega_pixel<VARIANT, FMA, MEM, BIG><<<grid, block, smem, ctx->stream>>>(args);
+            PT_CUDA(cudaGetLastError(), "launch k_mega_pixel");
+            if (diag) PT_CUDA(cudaMemcpyAsync(diag, args.cta_times, nb * 16, cudaMemcpyDeviceToDevice, ctx->stream), "copy CTA times");
+            return 0;
+        }
+    }
     k_mega_pixel<VARIANT, FMA, MEM, BIG><<<grid, block, smem, ctx->stream>>>(args);
     PT_CUDA(cudaGetLastError(), "launch k_mega_pixel");
     return 0;

@@ -146,6 +146,9 @@ extern "C" void pt_destroy(pt_ctx c) {
     cudaFree(c->d_cells); cudaFree(c->d_recs); cudaFree(c->d_refs); cudaFree(c->d_cell_start); cudaFree(c->d_sph); cudaFree(c->gb_kmax);
     cudaFree(c->gb_count); cudaFree(c->gb_raw_start); cudaFree(c->gb_cursor); cudaFree(c->gb_bsums); cudaFree(c->gb_raw_refs);
     cudaFree(c->d_rgba); cudaFree(c->d_accum); cudaFree(c->d_rng); cudaFree(c->d_counters); cudaFree(c->d_scratch);
+    cudaFree(c->d_tile_order); cudaFree(c->d_cta_times);
+    if (c->h_tile_order) cudaFreeHost(c->h_tile_order);
+    if (c->h_cta_times) cudaFreeHost(c->h_cta_times);
     cudaFree(c->d_vpls); cudaFree(c->d_vpl_active); cudaFree(c->d_vpl_count);
     if (c->wf_exec) cudaGraphExecDestroy(c->wf_exec);
     free(c->wf_key_args);
@@ -933,6 +936,15 @@ __global__ void __launch_bounds__(256) k_peak_issue(unsigned *out, int trips, fl
 
 // out[0] = measured FP32 TFLOP/s (FFMA = 2 flop), out[1] = FFMA warp instructions per second (G),
 // out[2] = warp instructions per second of the mixed FP32 + integer kernel (G), out[3] = its duration in ms
+// diagnostics: copy `bytes` of the context's scratch buffer (offset 256: per-CTA timing table of PT_CTA_TIMES=1) to the host
+extern "C" int pt_debug_read_scratch(pt_ctx c, void *dst, size_t offset, size_t bytes) {
+    if (!c || !dst || offset + bytes > c->scratch_cap) return pt_fail(1, "pt_debug_read_scratch: out of range");
+    PT_CUDA(cudaSetDevice(c->device), "select device");
+    PT_CUDA(cudaMemcpyAsync(dst, (char *)c->d_scratch + offset, bytes, cudaMemcpyDeviceToHost, c->stream), "read scratch");
+    PT_CUDA(cudaStreamSynchronize(c->stream), "sync");
+    return 0;
+}
+
 extern "C" int pt_measure_peaks(pt_ctx c, double out[4]) {
     if (!c || !out) return pt_fail(1, "pt_measure_peaks: null argument");
     PT_CUDA(cudaSetDevice(c->device), "select device");
