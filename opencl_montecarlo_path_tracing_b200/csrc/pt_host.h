@@ -107,6 +107,11 @@ struct pt_ctx_s {
     unsigned char tile_order_key[192];
     int tile_order_state;         // 0 none, 1 sorted from the 1-spp pre-pass, 2 a full launch is recording, 3 sorted from a full launch
 
+    // AUTO kernel choice of the brute-force variants: cached estimate of the pixels that scan the mesh
+    double mesh_est;
+    unsigned char mesh_est_key[96];
+    bool mesh_est_valid;
+
     // wavefront / persistent scratch
     void *d_scratch;
     size_t scratch_cap;
@@ -142,6 +147,7 @@ int pt_launch_wavefront(pt_ctx ctx, const pt_render_params *p, const pt::LaunchA
 int pt_launch_grid_tma(pt_ctx ctx, const pt_render_params *p, const pt::LaunchArgs &args);
 int pt_grid_build_device(pt_ctx ctx, const pt_grid *g);
 int pt_launch_stream_grid(pt_ctx ctx, const pt_render_params *p, const pt::LaunchArgs &args);
+int pt_launch_spec(pt_ctx ctx, const pt_render_params *p, const pt::LaunchArgs &args);
 int pt_launch_grid_pool(pt_ctx ctx, const pt_render_params *p, const pt::LaunchArgs &args);
 int pt_launch_bidir(pt_ctx ctx, const pt_render_params *p, const pt::LaunchArgs &args);
 int pt_launch_light_tracer_kernels(pt_ctx ctx, int arith, const pt::LaunchArgs &args, int n, float4 *vpl, uint4 *rng_out,

@@ -94,11 +94,11 @@ __global__ void __launch_bounds__(128, (BIG && VARIANT == PT_VARIANT_GRID) ? 8 :
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned long long t_start = 0;
-    if (BIG && GRID && P.cta_times && threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start));
+    if (BIG && P.cta_times && threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start));
     // tile of this CTA: its 2-D block index, or — 1-D launches of the big-grid kernel — entry blockIdx.x of the launch order
     // (longest tile first, see launch_pixel_b)
     uint32_t bx = blockIdx.x, by = blockIdx.y;
-    if (BIG && GRID && P.tile_order) {
+    if (BIG && P.tile_order) {
         const uint32_t tile = __ldg(P.tile_order + blockIdx.x);
         by = tile / P.tiles_x; bx = tile - by * P.tiles_x;
     }
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(128, (BIG && VARIANT == PT_VARIANT_GRID) ? 8 :
         if (P.rng_out) P.rng_out[pix] = make_uint4(rng.x0, rng.x1, rng.c0, rng.c1);
     }
     flush_counters(P, cnt, GRID ? 0 : S->ntri_counted, P.ap.nsq + P.ap.nsp);
-    if (BIG && GRID && P.cta_times && threadIdx.x == 0) {
+    if (BIG && P.cta_times && threadIdx.x == 0) {
         unsigned long long t_end;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_end));
         const size_t b = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
@@ -222,7 +222,7 @@ static int launch_pixel_b(pt_ctx ctx, const LaunchArgs &args_in) {
     if (smem > 48 * 1024)
         PT_CUDA(cudaFuncSetAttribute(k_mega_pixel<VARIANT, FMA, MEM, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                 "opt-in shared memory");
-    if (BIG && VARIANT == PT_VARIANT_GRID) {
+    if (BIG) {
         static int order = -1;
         if (order == -1) { const char *e = getenv("PT_TILE_ORDER"); order = e ? atoi(e) : 1; }
         const size_t n = (size_t)grid.x * grid.y;

@@ -23,6 +23,7 @@
 #include "pt_bidir.cuh"
 #include "pt_gridstream.cuh"
 #include "pt_gridpool.cuh"
+#include "pt_spec.cuh"
 
 // ------------------------------------------------------------------------------------ errors
 static std::atomic<int> g_error_mode{PT_ERRORS_EXIT};
@@ -581,18 +582,71 @@ static int fill_args(pt_ctx c, const pt_camera *cam, const pt_render_params *p, 
 }
 
 // PT_KERNEL_AUTO / PT_SCENE_AUTO: measured best per variant on B200
-static pt_render_params resolve_auto(const pt_render_params *in, int nrows) {
+// Estimated number of pixels of this launch that have to scan the brute-force mesh at all — what PT_KERNEL_SPEC's first
+// pass would queue: through a 48 x 48 grid of pixel centres (lens centre, no jitter; camera as base:233-236) the camera
+// ray, and the shadow lines from its floor hit to every light, against the mesh's bounding sphere (inflated by ~1 % of
+// the distance for lens blur and pixel footprint).  Only steers the kernel choice.
+static double estimate_mesh_pixels(pt_ctx c, const pt::LaunchArgs &A) {
+    if (!(c->mesh_r < 1e30f) || c->h_scene[0]->ntri == 0) return 0.0;
+    struct Key { int W, nrows, row_begin, row_end, stripe_h, rank, nranks; unsigned long long scene_version; pt::Camera cam; } key;
+    memset(&key, 0, sizeof(key));
+    key.W = A.W; key.nrows = A.nrows; key.row_begin = A.row_begin; key.row_end = A.row_end; key.stripe_h = A.stripe_h; key.rank = A.rank;
+    key.nranks = A.nranks; key.scene_version = c->scene_version; key.cam = A.cam;
+    static_assert(sizeof(Key) <= sizeof(c->mesh_est_key), "estimate key buffer too small");
+    if (c->mesh_est_valid && memcmp(&key, c->mesh_est_key, sizeof(key)) == 0) return c->mesh_est;
+    const int G = 48;
+    const double C[3] = {c->mesh_c[0], c->mesh_c[1], c->mesh_c[2]};
+    auto line_near = [&](const double o[3], const double d[3]) {           // d need not be normalised
+        double dd = 0.0, b = 0.0, oc2 = 0.0;
+        for (int a = 0; a < 3; ++a) { const double oc = C[a] - o[a]; dd += d[a] * d[a]; b += oc * d[a]; oc2 += oc * oc; }
+        if (dd == 0.0) return false;
+        const double dist2 = oc2 - b * b / dd, r = (double)c->mesh_r + 0.01 * sqrt(oc2);
+        return dist2 <= r * r;
+    };
+    int heavy = 0;
+    const pt::SceneBlock *hs = c->h_scene[0];
+    for (int gy = 0; gy < G; ++gy)
+        for (int gx = 0; gx < G; ++gx) {
+            const int vr = (int)((gy + 0.5) / G * A.nrows);
+            const double row = (double)pt::map_row(A, vr < A.nrows ? vr : A.nrows - 1) + 0.5, col = (gx + 0.5) / G * A.W;
+            double d[3];
+            for (int a = 0; a < 3; ++a) d[a] = (double)A.cam.right[a] * row + (double)A.cam.up[a] * col + (double)A.cam.eye[a];
+            const double o[3] = {17.0, 16.0, 8.0};
+            bool h = line_near(o, d);
+            if (!h && d[2] < 0.0) {                                        // floor hit: do its shadow lines pass the mesh?
+                const double t = -o[2] / d[2];
+                const double X[3] = {o[0] + t * d[0], o[1] + t * d[1], 0.0};
+                for (int l = 0; l < hs->nlights && !h; ++l) {
+                    const double ld[3] = {hs->lights[l].x + 0.5 - X[0], hs->lights[l].y + 0.5 - X[1], hs->lights[l].z - X[2]};
+                    h = line_near(X, ld);
+                }
+            }
+            heavy += h;
+        }
+    c->mesh_est = (double)heavy / (G * G) * (double)A.W * (double)A.nrows;
+    memcpy(c->mesh_est_key, &key, sizeof(key));
+    c->mesh_est_valid = true;
+    return c->mesh_est;
+}
+
+static pt_render_params resolve_auto(pt_ctx c, const pt_render_params *in, const pt::LaunchArgs &A) {
+    const int nrows = A.nrows;
     pt_render_params p = *in;
     if (p.kernel == PT_KERNEL_AUTO) {
         if (p.variant == PT_VARIANT_BIDIR) p.kernel = PT_KERNEL_MEGA;
         else if (p.variant == PT_VARIANT_NODOF) p.kernel = PT_KERNEL_MEGA;   // single-copy Sample(): 0.433 ms vs 0.479 ms persistent (512x512)
         else if (p.variant == PT_VARIANT_GRID) p.kernel = PT_KERNEL_MEGA;
         else {
-            // brute-force triangle scenes: a pixel that sees the mesh is a ~1.7 ms serial chain at 64 spp.  Small
-            // frames are bounded by that tail -> scatter heavy pixels over warps (persistent + cooperative scan);
-            // large frames have enough heavy tiles to fill the GPU, where the dense lane-serial scan is cheaper.
-            const long long pixels = (long long)p.width * nrows;     // the launch's own share, not the full frame
-            p.kernel = pixels <= 400000 ? PT_KERNEL_PERSISTENT : PT_KERNEL_MEGA;
+            // brute-force triangle scenes: a pixel that sees the mesh is a ~1.7 ms serial chain at 64 spp.  While the mesh
+            // covers few pixels the frame is bounded by those chains -> PT_KERNEL_SPEC traces 32 samples of such a pixel at
+            // once (512x512 default scene 0.89 ms vs 1.76 persistent, 2.20 mega).  With enough heavy pixels to fill the GPU
+            // (torus at 512x512: half the frame; any 1080p frame) the thread-per-pixel megakernel's dense lane-serial scan
+            // is the cheaper form (1.17 vs 2.02 ms; 20.6 vs 31.1 ms per 256 spp at 1080p).
+            static double thresh = -1.0;
+            if (thresh < 0.0) { const char *e = getenv("PT_SPEC_MAX_MESH_PIXELS"); thresh = e ? atof(e) : 50000.0; }
+            const double mesh_pixels = estimate_mesh_pixels(c, A);
+            if (getenv("PT_DEBUG_AUTO")) fprintf(stderr, "ptcuda: AUTO %dx%d rows: estimated mesh pixels %.0f (threshold %.0f)\n", p.width, nrows, mesh_pixels, thresh);
+            p.kernel = mesh_pixels <= thresh ? PT_KERNEL_SPEC : PT_KERNEL_MEGA;
         }
     }
     if (p.scene_mem == PT_SCENE_AUTO)
@@ -601,7 +655,7 @@ static pt_render_params resolve_auto(const pt_render_params *in, int nrows) {
 }
 
 static int dispatch(pt_ctx c, const pt_render_params *pin, const pt::LaunchArgs &A) {
-    const pt_render_params resolved = resolve_auto(pin, A.nrows);
+    const pt_render_params resolved = resolve_auto(c, pin, A);
     const pt_render_params *p = &resolved;
     DevLock lock(c->device);     // constant-scene bind + launch are one critical section per device
     PT_CUDA(cudaMemsetAsync(c->d_counters, 0, 8 * sizeof(unsigned long long), c->stream), "clear counters");
@@ -616,6 +670,7 @@ static int dispatch(pt_ctx c, const pt_render_params *pin, const pt::LaunchArgs 
         case PT_KERNEL_GRID_STREAM:
             if (p->variant != PT_VARIANT_GRID) return pt_fail(1, "PT_KERNEL_GRID_STREAM applies to the trianglegrid variant only");
             return pt_launch_stream_grid(c, p, A);
+        case PT_KERNEL_SPEC: return pt_launch_spec(c, p, A);
         case PT_KERNEL_GRID_POOL:
             if (p->variant != PT_VARIANT_GRID) return pt_fail(1, "PT_KERNEL_GRID_POOL applies to the trianglegrid variant only");
             return pt_launch_grid_pool(c, p, A);
