@@ -587,7 +587,8 @@ static int fill_args(pt_ctx c, const pt_camera *cam, const pt_render_params *p, 
 // ray, and the shadow lines from its floor hit to every light, against the mesh's bounding sphere (inflated by ~1 % of
 // the distance for lens blur and pixel footprint).  Only steers the kernel choice.
 static double estimate_mesh_pixels(pt_ctx c, const pt::LaunchArgs &A) {
-    if (!(c->mesh_r < 1e30f) || c->h_scene[0]->ntri == 0) return 0.0;
+    if (c->h_scene[0]->ntri == 0) return 0.0;
+    if (!(A.ap.mesh_r < 1e30f)) return (double)A.W * (double)A.nrows;      // no mesh cull (no_cull, or no finite sphere): every ray scans
     struct Key { int W, nrows, row_begin, row_end, stripe_h, rank, nranks; unsigned long long scene_version; pt::Camera cam; } key;
     memset(&key, 0, sizeof(key));
     key.W = A.W; key.nrows = A.nrows; key.row_begin = A.row_begin; key.row_end = A.row_end; key.stripe_h = A.stripe_h; key.rank = A.rank;
