@@ -536,6 +536,8 @@ class Ours:
             step()
         torch.cuda.synchronize()
         counters = r.counters()                      # this rank's share of the frame
+        resolved_kernel = r.last_kernel()
+        launches_per_render = {"spec": 2}.get(resolved_kernel, 1)     # PT_KERNEL_SPEC = light pass + heavy pass
         if world > 1:
             dist.barrier()
         sampler = None
@@ -702,7 +704,7 @@ class Ours:
             "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": ("strong" if strong else "weak") if world > 1 else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(w, wname, W, H, spp), kernel=args.kernel, scene_mem=args.scene_mem or "auto",
+            "config": dict(workload_config(w, wname, W, H, spp), kernel=args.kernel, kernel_resolved=resolved_kernel, scene_mem=args.scene_mem or "auto",
                            arith="fma (bit-exact vs oracle -DPT_CONTRACT=1)", l2="flushed between timed steps (256 MiB write)",
                            sharding=(("sample blocks (spp/N samples of every pixel per rank, re-seeded streams) + one NCCL reduce" if by_samples
                                       else "8-row stripes round-robin over ranks + one NCCL reduce of the float accumulation buffer")
@@ -710,7 +712,7 @@ class Ours:
             "msamples_per_s": samples / 1e3 / ms_per_step, "rays_per_step": rays, "samples_per_step": samples,
             "e2e": {"value": rays / 1e3 / e2e_ms, "unit": "Mrays/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "api": e2e_api},
-            "gpu_launches": steps * ((1 + (2 if bidir else 0)) * world + (1 if world > 1 else 0)),
+            "gpu_launches": steps * ((launches_per_render + (2 if bidir else 0)) * world + (1 if world > 1 else 0)),
             "parity_check": parity,
             "roofline": roof,
         }

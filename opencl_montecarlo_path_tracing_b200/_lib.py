@@ -143,6 +143,8 @@ PTCUDA_SYMBOLS = {
     "pt_selftest_fastmath": (_I, [_VP, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)]),
     "pt_probe_rng": (_I, [_VP, _U32P, C.c_uint32, _I, _FP, _U32P]),
     "pt_measure_peaks": (_I, [_VP, C.POINTER(C.c_double)]),
+    "pt_last_kernel": (_I, [_VP]),
+    "pt_query_device": (_I, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p, C.c_size_t]),
     "pt_debug_read_scratch": (_I, [_VP, C.c_void_p, C.c_size_t, C.c_size_t]),
 }
 

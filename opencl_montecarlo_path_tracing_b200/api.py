@@ -317,6 +317,11 @@ class Renderer:
         _check(self._l.pt_get_counters(self.ctx, C.byref(cnt)), "pt_get_counters")
         return cnt.as_dict()
 
+    def last_kernel(self):
+        """Name of the kernel flavour the most recent render resolved to (what "auto" picked)."""
+        k = self._l.pt_last_kernel(self.ctx)
+        return {v: n for n, v in _lib.PT_KERNEL.items()}.get(k, str(k))
+
     def synchronize(self):
         _check(self._l.pt_synchronize(self.ctx), "pt_synchronize")
 

@@ -4,6 +4,7 @@
 
 #include <float.h>
 #include <math.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -32,23 +33,133 @@ int pth_parse_bitmap(const char *path, int32_t rows[9]) {
     return n;
 }
 
+/* ---- triangles.txt --------------------------------------------------------------------------------------------------
+ * The reference reads it with unchecked fgets() + atof(), 13 lines per triangle (3 x (x, y, z, blank) + blank), in a
+ * `while (!feof(f) && n < MAX_TRIANGLES)` loop (CLSuperPathTracer.c:62-107).  A million triangles are 13.6 M lines, so
+ * the file is read into memory once and the triangles whose 13 lines are all complete are converted on several threads
+ * — with the SAME conversion, atof() on a private copy of each line — while the end of the file (where fgets() starts
+ * returning short or no lines and the reference replays stale buffers) runs through a byte-exact emulation of the loop. */
+struct mem_file { const char *p; size_t size, pos; int eof; };
+
+/* fgets(buf, LINE_MAX_LEN, f) on the memory image, unchecked: buf keeps its content when nothing is left */
+static void mem_next_line(struct mem_file *m, char *buf) {
+    if (m->pos >= m->size) { m->eof = 1; return; }
+    size_t n = 0;
+    while (n < LINE_MAX_LEN - 1 && m->pos < m->size) {
+        const char c = m->p[m->pos++];
+        buf[n++] = c;
+        if (c == '\n') break;
+    }
+    buf[n] = 0;
+    if (n > 0 && buf[n - 1] != '\n' && n < LINE_MAX_LEN - 1) m->eof = 1;     /* ran into the end of the file while reading */
+}
+
+static float line_to_float(const char *line, size_t len) {
+    char tmp[LINE_MAX_LEN];
+    if (len > LINE_MAX_LEN - 1) len = LINE_MAX_LEN - 1;
+    memcpy(tmp, line, len);
+    tmp[len] = 0;
+    return (float)atof(tmp);
+}
+
+struct tri_job {
+    const char *buf;
+    const size_t *start;      /* byte offset of the first line of every bulk triangle */
+    size_t t0, t1;
+    float *tris;
+    float lo[3], hi[3];
+};
+
+static void *tri_worker(void *arg) {
+    struct tri_job *j = (struct tri_job *)arg;
+    for (int a = 0; a < 3; ++a) { j->lo[a] = FLT_MAX; j->hi[a] = FLT_MIN; }
+    for (size_t n = j->t0; n < j->t1; ++n) {
+        const char *p = j->buf + j->start[n];
+        float *t = j->tris + 12 * n;
+        for (int v = 0; v < 3; ++v) {
+            for (int a = 0; a < 3; ++a) {
+                const char *e = (const char *)strchr(p, '\n');          /* every line of a bulk triangle is complete */
+                const float c = line_to_float(p, (size_t)(e - p) + 1);
+                if (c < j->lo[a]) j->lo[a] = c;
+                if (c > j->hi[a]) j->hi[a] = c;
+                t[4 * v + a] = c;
+                p = e + 1;
+            }
+            t[4 * v + 3] = 0.0f;
+            p = strchr(p, '\n') + 1;                                     /* blank line closing the vertex */
+        }
+    }
+    return NULL;
+}
+
 int pth_parse_triangles(const char *path, int max_triangles, float **out, float box_min[4], float box_max[4]) {
-    FILE *f = fopen(path, "r");
+    FILE *f = fopen(path, "rb");
     if (!f) return -1;
-    size_t cap = 1024;
+    fseek(f, 0, SEEK_END);
+    const long fsize = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    char *buf = (char *)malloc((size_t)(fsize > 0 ? fsize : 0) + 1);
+    const size_t size = fsize > 0 ? fread(buf, 1, (size_t)fsize, f) : 0;
+    fclose(f);
+    buf[size] = 0;
+
+    /* complete lines, and where every 13th starts; an over-long line (fgets would split it) or a NUL byte (string functions
+     * would stop at it) sends the whole file through the emulation instead */
+    size_t nlines = 0, ntri_lines = 0, cap_starts = 1024, nstarts = 0;
+    size_t *start = (size_t *)malloc(cap_starts * sizeof(size_t));
+    int plain = memchr(buf, 0, size) == NULL;
+    for (size_t pos = 0; pos < size && plain;) {
+        const char *e = (const char *)memchr(buf + pos, '\n', size - pos);
+        if (!e) break;
+        if ((size_t)(e - (buf + pos)) + 1 > LINE_MAX_LEN - 1) { plain = 0; break; }
+        if (nlines % 13 == 0) {
+            if (nstarts == cap_starts) { cap_starts *= 2; start = (size_t *)realloc(start, cap_starts * sizeof(size_t)); }
+            start[nstarts++] = pos;
+        }
+        ++nlines;
+        pos = (size_t)(e - buf) + 1;
+    }
+    ntri_lines = plain ? nlines / 13 : 0;
+    size_t nbulk = ntri_lines < (size_t)(max_triangles > 0 ? max_triangles : 0) ? ntri_lines : (size_t)(max_triangles > 0 ? max_triangles : 0);
+    if (nbulk > 0) --nbulk;          /* the last complete triangle goes through the emulation: it leaves the line buffers as the loop would */
+
+    size_t cap = nbulk + 1024;
     float *tris = (float *)malloc(cap * 12 * sizeof(float));
     float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX};
     float hi[3] = {FLT_MIN, FLT_MIN, FLT_MIN};   /* smallest positive float, as the reference */
+    if (nbulk > 0) {
+        long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
+        int nth = (int)(ncpu < 1 ? 1 : (ncpu > 16 ? 16 : ncpu));
+        if ((size_t)nth > nbulk / 4096 + 1) nth = (int)(nbulk / 4096 + 1);
+        struct tri_job jobs[16];
+        pthread_t th[16];
+        int started[16] = {0};
+        for (int k = 0; k < nth; ++k) {
+            jobs[k].buf = buf; jobs[k].start = start; jobs[k].tris = tris;
+            jobs[k].t0 = nbulk * (size_t)k / (size_t)nth; jobs[k].t1 = nbulk * (size_t)(k + 1) / (size_t)nth;
+            if (k > 0) started[k] = pthread_create(&th[k], NULL, tri_worker, &jobs[k]) == 0;
+        }
+        tri_worker(&jobs[0]);
+        for (int k = 1; k < nth; ++k) { if (started[k]) pthread_join(th[k], NULL); else tri_worker(&jobs[k]); }
+        for (int k = 0; k < nth; ++k)
+            for (int a = 0; a < 3; ++a) {
+                if (jobs[k].lo[a] < lo[a]) lo[a] = jobs[k].lo[a];
+                if (jobs[k].hi[a] > hi[a]) hi[a] = jobs[k].hi[a];
+            }
+    }
+
+    /* the reference's loop, from triangle nbulk on */
+    struct mem_file m = {buf, size, nbulk > 0 ? start[nbulk] : 0, 0};
     char coord[3][LINE_MAX_LEN] = {"", "", ""};
-    int n = 0;
-    while (!feof(f) && n < max_triangles) {
-        if ((size_t)n == cap) {
+    size_t n = nbulk;
+    while (!m.eof && n < (size_t)(max_triangles > 0 ? max_triangles : 0)) {
+        if (n == cap) {
             cap *= 2;
             tris = (float *)realloc(tris, cap * 12 * sizeof(float));
         }
-        float *t = tris + 12 * (size_t)n;
+        float *t = tris + 12 * n;
         for (int v = 0; v < 3; ++v) {
-            for (int a = 0; a < 3; ++a) next_line(f, coord[a]);
+            for (int a = 0; a < 3; ++a) mem_next_line(&m, coord[a]);
             for (int a = 0; a < 3; ++a) {
                 float c = (float)atof(coord[a]);
                 if (c < lo[a]) lo[a] = c;
@@ -56,12 +167,13 @@ int pth_parse_triangles(const char *path, int max_triangles, float **out, float 
                 t[4 * v + a] = c;
             }
             t[4 * v + 3] = 0.0f;
-            next_line(f, coord[0]);         /* blank line closing the vertex */
+            mem_next_line(&m, coord[0]);    /* blank line closing the vertex */
         }
-        next_line(f, coord[0]);             /* blank line closing the triangle */
+        mem_next_line(&m, coord[0]);        /* blank line closing the triangle */
         ++n;
     }
-    fclose(f);
+    free(start);
+    free(buf);
     for (int a = 0; a < 3; ++a) {
         if (box_min) box_min[a] = lo[a];
         if (box_max) box_max[a] = hi[a];
@@ -69,7 +181,7 @@ int pth_parse_triangles(const char *path, int max_triangles, float **out, float 
     if (box_min) box_min[3] = 0.0f;
     if (box_max) box_max[3] = 0.0f;
     *out = tris;
-    return n;
+    return (int)n;
 }
 
 int pth_parse_lights(const char *path, float lights[5][4], int print_lights) {

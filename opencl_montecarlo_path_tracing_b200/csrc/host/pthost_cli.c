@@ -25,12 +25,53 @@
  *   PT_STATS=1         append Mrays/s, samples/s and work counters after the reference's own lines
  */
 #define _GNU_SOURCE
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
 
 #include "pthost.h"
+
+/* PT_TIMING=1: wall-clock of the host-side phases on stderr (stdout stays the reference's) */
+static double g_t0, g_tlast;
+static double wall_ms(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec / 1e6;
+}
+static void tick(const char *what) {
+    if (!getenv("PT_TIMING")) return;
+    const double now = wall_ms();
+    fprintf(stderr, "PT_TIMING %-28s %9.1f ms  (at %9.1f ms)\n", what, now - g_tlast, now - g_t0);
+    g_tlast = now;
+}
+
+/* CUDA initialisation (1.3 s per device, 8 devices + the NCCL communicators several seconds) does not depend on the scene:
+ * it runs on a helper thread while the main thread prints and parses triangles.txt. */
+struct create_job {
+    int ngpus;
+    int dev_count, dev, query_rc;
+    char dev_name[256];
+    int info_ready;
+    pthread_mutex_t lock;
+    pthread_cond_t cond;
+    pt_multi multi;
+    pt_ctx ctx;
+};
+static void *create_worker(void *arg) {
+    struct create_job *j = (struct create_job *)arg;
+    int count = 0, dev = 0;
+    const int rc = pt_query_device(&count, &dev, j->dev_name, sizeof(j->dev_name));
+    pthread_mutex_lock(&j->lock);
+    j->dev_count = count; j->dev = dev; j->query_rc = rc; j->info_ready = 1;
+    pthread_cond_signal(&j->cond);
+    pthread_mutex_unlock(&j->lock);
+    if (rc || dev < 0 || dev >= count) return NULL;            /* the main thread reports it, as select_device does */
+    if (j->ngpus > 1) j->multi = pt_multi_create(j->ngpus);
+    else j->ctx = pt_create(dev);
+    return NULL;
+}
 
 static int env_choice(const char *name, const char *const *opts, int nopts, int dflt) {
     const char *v = getenv(name);
@@ -42,6 +83,7 @@ static int env_choice(const char *name, const char *const *opts, int nopts, int 
 }
 
 int pth_cli_main(int variant, int argc, char **argv) {
+    g_t0 = g_tlast = wall_ms();
     int img_width = 512, img_height = 512;
     float cell_size_modifier = 3.0f;
     const int grid = variant == PT_VARIANT_GRID, nodof = variant == PT_VARIANT_NODOF, bidir = variant == PT_VARIANT_BIDIR;
@@ -61,13 +103,39 @@ int pth_cli_main(int variant, int argc, char **argv) {
     if (grid && argc > 3) cell_size_modifier = (float)atof(argv[3]);
     if (bidir && argc > 3) n_vlp = atoi(argv[3]);
 
-    /* select_platform / select_device / create_* of ocl_boiler.h */
+    /* select_platform / select_device / create_* of ocl_boiler.h: on a helper thread, started before anything else */
+    const int ngpus = getenv("PT_GPUS") ? atoi(getenv("PT_GPUS")) : 1;
+    struct create_job job;
+    memset(&job, 0, sizeof(job));
+    job.ngpus = ngpus;
+    pthread_mutex_init(&job.lock, NULL);
+    pthread_cond_init(&job.cond, NULL);
+    pthread_t creator;
+    const int threaded = pthread_create(&creator, NULL, create_worker, &job) == 0;
+    if (!threaded) create_worker(&job);
+
+    /* ... while this thread already reads triangles.txt (a million triangles are 13.6 M text lines); what the reference
+     * prints about them comes later, in its order */
+    int max_triangles = grid ? 65536 : 512;     /* MAX_TRIANGLES of the respective host */
+    if (getenv("PT_MAX_TRIANGLES")) max_triangles = atoi(getenv("PT_MAX_TRIANGLES"));
+    float *tris = NULL;
+    float box_min[4], box_max[4];
+    const int ntriangles_parsed = pth_parse_triangles("triangles.txt", max_triangles, &tris, box_min, box_max);
+    tick("parse triangles.txt");
+
+    pthread_mutex_lock(&job.lock);
+    while (!job.info_ready) pthread_cond_wait(&job.cond, &job.lock);
+    pthread_mutex_unlock(&job.lock);
     printf("number of platforms: %u\n", 1u);
     printf("selected platform %d: %s\n", 0, "NVIDIA CUDA (libptcuda, sm_100a)");
-    int dev = pt_select_device();
-    const int ngpus = getenv("PT_GPUS") ? atoi(getenv("PT_GPUS")) : 1;
-    pt_multi multi = ngpus > 1 ? pt_multi_create(ngpus) : NULL;
-    pt_ctx ctx = multi ? NULL : pt_create(dev);
+    if (job.query_rc) pt_check(job.query_rc, "counting devices");
+    printf("number of devices: %u\n", (unsigned)job.dev_count);
+    if (job.dev < 0 || job.dev >= job.dev_count) {
+        fprintf(stderr, "no device number %u", (unsigned)job.dev);
+        exit(1);
+    }
+    printf("selected device %d: %s\n", job.dev, job.dev_name);
+    tick("device query");
     time_t now = time(NULL);
     printf("compiling:\n// %s#include \"%s\"\n", ctime(&now), bidir ? "bidirectionalpathtracer.ocl" : "pathtracer.ocl");
     printf("=== BUILD LOG ===\n%s\n=========\n", "kernels are precompiled CUDA for sm_100a (libptcuda.so); nothing to build\n");
@@ -88,8 +156,6 @@ int pth_cli_main(int variant, int argc, char **argv) {
 
     pt_scene scene;
     memset(&scene, 0, sizeof(scene));
-    int max_triangles = grid ? 65536 : 512;     /* MAX_TRIANGLES of the respective host */
-    if (getenv("PT_MAX_TRIANGLES")) max_triangles = atoi(getenv("PT_MAX_TRIANGLES"));
     if (pth_parse_bitmap("spheres.txt", scene.spheres) < 0) pt_check(1, "open spheres.txt");
     const char *squares_file = "squares.txt";
     if (nodof) {
@@ -99,11 +165,9 @@ int pth_cli_main(int variant, int argc, char **argv) {
     }
     if (pth_parse_bitmap(squares_file, scene.squares) < 0) pt_check(1, "open %s", squares_file);
 
-    float *tris = NULL;
-    float box_min[4], box_max[4];
     pt_grid gdesc;
     memset(&gdesc, 0, sizeof(gdesc));
-    scene.ntriangles = pth_parse_triangles("triangles.txt", max_triangles, &tris, box_min, box_max);
+    scene.ntriangles = ntriangles_parsed;
     if (scene.ntriangles < 0) pt_check(1, "open triangles.txt");
     scene.triangles = tris;
     if (grid) {
@@ -117,9 +181,16 @@ int pth_cli_main(int variant, int argc, char **argv) {
     printf("Number of triangles: %d\n", scene.ntriangles);
     printf("Number of lights: %d\n", scene.nlights);
 
+    if (threaded) pthread_join(creator, NULL);
+    pt_multi multi = job.multi;
+    pt_ctx ctx = job.ctx;
+    if (ngpus > 1 ? !multi : !ctx) pt_check(1, "create the CUDA context(s)");
+    tick("wait for the context(s)");
     if (multi) pt_multi_set_scene(multi, &scene); else pt_set_scene(ctx, &scene);
+    tick("upload scene");
     pt_event grid_evt = NULL;
     if (grid) grid_evt = multi ? pt_multi_build_grid(multi, &gdesc) : pt_build_grid(ctx, &gdesc);
+    tick("build grid (enqueue)");
 
     static const char *const kernels[] = {"mega", "persistent", "wavefront", "auto", "grid_tma", "grid_stream", "grid_pool", "spec"};
     static const char *const mems[] = {"const", "smem", "auto"};
@@ -154,11 +225,13 @@ int pth_cli_main(int variant, int argc, char **argv) {
         pt_wait(w);
         pt_release_event(w);
     }
+    tick("warm-up launch");
     if (bidir && !light_evt)
         light_evt = multi ? pt_multi_launch_lighttracer(multi, n_vlp, seeds, rp.arith) : pt_launch_lighttracer(ctx, n_vlp, seeds, rp.arith);
     pt_event render_evt = multi ? pt_multi_launch_pathtracer(multi, &cam, &rp) : pt_launch_pathtracer(ctx, &cam, &rp);
     pt_event read_evt = NULL;
     void *pixels = multi ? pt_multi_map_render(multi, &read_evt) : pt_map_render(ctx, &read_evt);
+    tick("render + read back");
 
     const char *image_name = "result.ppm";
     if (pth_save_pam(image_name, img_width, img_height, pixels) != 0) {
@@ -170,6 +243,7 @@ int pth_cli_main(int variant, int argc, char **argv) {
     if (extra && strstr(extra, "png") && pth_save_png("result.png", img_width, img_height, pixels)) pt_check(1, "write result.png");
     if (extra && strstr(extra, "ppm") && pth_save_ppm("result_p6.ppm", img_width, img_height, pixels)) pt_check(1, "write result_p6.ppm");
 
+    tick("write image");
     double render_ms = pt_runtime_ms(render_evt), read_ms = pt_runtime_ms(read_evt), light_ms = 0.0;
     if (bidir) {
         light_ms = pt_runtime_ms(light_evt);
@@ -211,5 +285,6 @@ int pth_cli_main(int variant, int argc, char **argv) {
     pt_release_event(light_evt);
     free(tris);
     if (multi) pt_multi_destroy(multi); else pt_destroy(ctx);
+    tick("destroy");
     return 0;
 }

@@ -90,6 +90,7 @@ struct pt_ctx_s {
     size_t h_rgba_cap;
     unsigned long long *d_counters;
     int last_w, last_h, last_variant;
+    int last_kernel;              // PT_KERNEL_* the most recent render resolved to (after PT_KERNEL_AUTO)
     int accum_valid_w, accum_valid_h;   // extent of d_accum the most recent launch wrote (0: it did not request it)
     size_t rng_valid_items;             // work-items of d_rng the most recent launch wrote
 

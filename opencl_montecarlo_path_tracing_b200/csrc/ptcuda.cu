@@ -12,7 +12,10 @@
 
 #include <atomic>
 #include <mutex>
+#include <thread>
+#include <vector>
 #include <new>
+#include <string>
 
 #include "pt_host.h"
 #include "pt_mega.cuh"
@@ -68,6 +71,29 @@ extern "C" int pt_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
     return n;
+}
+
+// select_device of ocl_boiler.h without the printing: number of devices, the index PT_DEVICE / OCL_DEVICE selects (not
+// range-checked) and that device's name.  Lets a host start CUDA on a helper thread and print when it is ready.
+extern "C" int pt_query_device(int *count, int *selected, char *name, size_t name_len) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return pt_cuda_fail(e, "counting devices");
+    const char *env = getenv("PT_DEVICE");
+    if (!env || !env[0]) env = getenv("OCL_DEVICE");
+    const int d = (env && env[0]) ? atoi(env) : 0;
+    if (count) *count = n;
+    if (selected) *selected = d;
+    if (name && name_len) {
+        name[0] = 0;
+        if (d >= 0 && d < n) {
+            cudaDeviceProp prop;
+            e = cudaGetDeviceProperties(&prop, d);
+            if (e != cudaSuccess) return pt_cuda_fail(e, "device name");
+            snprintf(name, name_len, "%s", prop.name);
+        }
+    }
+    return 0;
 }
 
 extern "C" int pt_select_device(void) {
@@ -658,6 +684,7 @@ static pt_render_params resolve_auto(pt_ctx c, const pt_render_params *in, const
 static int dispatch(pt_ctx c, const pt_render_params *pin, const pt::LaunchArgs &A) {
     const pt_render_params resolved = resolve_auto(c, pin, A);
     const pt_render_params *p = &resolved;
+    c->last_kernel = p->kernel;
     DevLock lock(c->device);     // constant-scene bind + launch are one critical section per device
     PT_CUDA(cudaMemsetAsync(c->d_counters, 0, 8 * sizeof(unsigned long long), c->stream), "clear counters");
     if (A.nrows <= 0) return 0;
@@ -992,6 +1019,8 @@ __global__ void __launch_bounds__(256) k_peak_issue(unsigned *out, int trips, fl
 
 // out[0] = measured FP32 TFLOP/s (FFMA = 2 flop), out[1] = FFMA warp instructions per second (G),
 // out[2] = warp instructions per second of the mixed FP32 + integer kernel (G), out[3] = its duration in ms
+extern "C" int pt_last_kernel(pt_ctx c) { return c ? c->last_kernel : -1; }
+
 // diagnostics: copy `bytes` of the context's scratch buffer (offset 256: per-CTA timing table of PT_CTA_TIMES=1) to the host
 extern "C" int pt_debug_read_scratch(pt_ctx c, void *dst, size_t offset, size_t bytes) {
     if (!c || !dst || offset + bytes > c->scratch_cap) return pt_fail(1, "pt_debug_read_scratch: out of range");
@@ -1108,16 +1137,41 @@ static int nccl_load(pt_nccl_api *a) {
 
 extern "C" void pt_multi_destroy(pt_multi m);
 
+// run f(i) for i = 0..n-1 on n host threads (one per device: CUDA context creation, scene uploads and grid builds of the
+// devices are independent and each takes a noticeable fraction of a second); returns the first non-zero result
+template <class F>
+static int for_each_device(int n, F f) {
+    std::vector<int> rc((size_t)n, 0);
+    std::vector<std::string> msg((size_t)n);
+    std::vector<std::thread> th;
+    for (int i = 1; i < n; ++i)
+        th.emplace_back([&, i] {
+            rc[(size_t)i] = f(i);
+            if (rc[(size_t)i]) msg[(size_t)i] = g_last_error;      // the message lives in the worker's thread-local buffer
+        });
+    rc[0] = f(0);
+    for (auto &t : th) t.join();
+    for (int i = 0; i < n; ++i)
+        if (rc[(size_t)i]) {
+            if (i > 0) snprintf(g_last_error, sizeof(g_last_error), "%s", msg[(size_t)i].c_str());
+            return rc[(size_t)i];
+        }
+    return 0;
+}
+
 extern "C" pt_multi pt_multi_create(int ngpus) {
     if (ngpus < 1 || ngpus > 16 || ngpus > pt_device_count()) { pt_fail(1, "pt_multi_create: %d GPUs requested, %d visible", ngpus, pt_device_count()); return nullptr; }
     pt_multi m = (pt_multi)calloc(1, sizeof(pt_multi_s));
     m->n = ngpus;
-    for (int i = 0; i < ngpus; ++i) {
-        m->ctx[i] = pt_create(i);
-        if (!m->ctx[i]) { pt_multi_destroy(m); return nullptr; }       // releases the contexts created so far
-    }
+    // the contexts (CUDA initialisation of every device) in parallel, the NCCL library load beside them
+    int nccl_rc = 0;
+    std::thread loader;
+    if (ngpus > 1) loader = std::thread([&] { nccl_rc = nccl_load(&m->nccl); });
+    const int crc = for_each_device(ngpus, [&](int i) { m->ctx[i] = pt_create(i); return m->ctx[i] ? 0 : 1; });
+    if (loader.joinable()) loader.join();
+    if (crc) { pt_multi_destroy(m); return nullptr; }           // releases the contexts created so far
     if (ngpus > 1) {
-        if (nccl_load(&m->nccl)) { pt_multi_destroy(m); return nullptr; }
+        if (nccl_rc) { pt_multi_destroy(m); return nullptr; }
         int devs[16];
         for (int i = 0; i < ngpus; ++i) devs[i] = i;
         int rc = m->nccl.CommInitAll(m->comms, ngpus, devs);
@@ -1144,21 +1198,16 @@ extern "C" void pt_multi_destroy(pt_multi m) {
 }
 
 extern "C" int pt_multi_set_scene(pt_multi m, const pt_scene *scene) {
-    for (int i = 0; i < m->n; ++i) {
-        int rc = pt_set_scene(m->ctx[i], scene);     // the scene is replicated on every device
-        if (rc) return rc;
-    }
-    return 0;
+    // the scene is replicated on every device; the uploads (pageable host memory -> staged copies) run side by side
+    return for_each_device(m->n, [&](int i) { return pt_set_scene(m->ctx[i], scene); });
 }
 
 extern "C" pt_event pt_multi_build_grid(pt_multi m, const pt_grid *grid) {
-    pt_event first = nullptr;
-    for (int i = 0; i < m->n; ++i) {
-        pt_event e = pt_build_grid(m->ctx[i], grid);
-        if (!e) return nullptr;
-        if (i == 0) first = e; else pt_release_event(e);
-    }
-    return first;
+    pt_event ev[16] = {nullptr};
+    const int rc = for_each_device(m->n, [&](int i) { ev[i] = pt_build_grid(m->ctx[i], grid); return ev[i] ? 0 : 1; });
+    for (int i = 1; i < m->n; ++i) pt_release_event(ev[i]);
+    if (rc) { pt_release_event(ev[0]); return nullptr; }
+    return ev[0];
 }
 
 // every device traces the (tiny) light pass itself: identical seeds -> identical VPL buffers, no exchange needed

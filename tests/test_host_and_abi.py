@@ -105,6 +105,43 @@ def test_parser_quirks(tmp_path, oracle_sep):
         pt.load_scene_dir(os.path.join(d, "nope"), "base")
 
 
+def test_threaded_triangle_parser_equals_the_fgets_loop(tmp_path, oracle_sep):
+    """pth_parse_triangles converts the complete 13-line records of a big file on several threads and emulates fgets()/feof()
+    on the rest; the oracle's reader is the reference's sequential FILE loop (CLSuperPathTracer.c:62-107).  Same floats, same
+    count, same bounding box on files with every kind of ending, stray blank lines, odd tokens and over-long lines."""
+    import gen_mesh
+    import write_scenes
+    d = str(tmp_path)
+    write_scenes.write_variant("base", d)
+    tris = gen_mesh.soup(20000, seed=9, box_size=20.0)
+    path = os.path.join(d, "triangles.txt")
+    write_scenes.write_triangles(path, tris[:, [0, 1, 2, 4, 5, 6, 8, 9, 10]])
+    clean = open(path).read()
+    lines = clean.split("\n")
+    variants = {
+        "as written (no trailing newline)": clean,
+        "trailing newline": clean + "\n",
+        "complete 13-line tail": clean + "\n\n\n",
+        "cut in the middle of a record": "\n".join(lines[: 13 * 15000 + 5]),
+        "cut in the middle of a number": clean[: len(clean) // 2 + 3],
+        "a stray blank line shifts every later record": "\n".join(lines[:1000] + [""] + lines[1000:]),
+        "tokens atof reads differently": clean.replace(lines[7], " +1.5e0xyz", 1).replace(lines[20], "nan", 1).replace(lines[33], "0x1p3", 1),
+        "one over-long line": "\n".join(lines[:50] + ["9" * 700] + lines[51:]),
+        "empty file": "",
+        "a single newline": "\n",
+        "carriage returns": clean[:5000].replace("\n", "\r\n"),
+    }
+    for name, text in variants.items():
+        open(path, "w").write(text)
+        for cap in (65536, 15001, 1):
+            mine = pt.load_scene_dir(d, "grid", max_triangles=cap)
+            ref = oracle_sep.load_scene_dir(d, "grid", max_triangles=cap)
+            assert mine.ntriangles == ref["triangles"].shape[0], (name, cap, mine.ntriangles, ref["triangles"].shape[0])
+            assert np.array_equal(mine.triangles.view(np.uint32), ref["triangles"].view(np.uint32)), (name, cap)
+            assert np.array_equal(mine.box_min.view(np.uint32), ref["box_min"].view(np.uint32)), (name, cap)
+            assert np.array_equal(mine.box_max.view(np.uint32), ref["box_max"].view(np.uint32)), (name, cap)
+
+
 def test_camera_and_grid_dims_match_oracle_and_golden(scene_dirs, oracle_sep):
     g = json.load(open(os.path.join(G, "golden_host.json")))
     cam = pt.camera()

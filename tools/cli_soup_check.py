@@ -17,11 +17,12 @@ tris = gen_mesh.soup(1 << 20)
 write_scenes.write_triangles(os.path.join(d, "triangles.txt"), tris[:, [0, 1, 2, 4, 5, 6, 8, 9, 10]])
 print("scene written in %.1f s (%.0f MB)" % (time.time() - t0, os.path.getsize(os.path.join(d, "triangles.txt")) / 1e6), flush=True)
 digests = {}
-for g in (1, n):
-    env = dict(os.environ, PT_SEEDS="1,2,3,4", PT_GPUS=str(g), PT_SPP=spp, PT_MAX_TRIANGLES=str(1 << 20), PT_STATS="1")
+for g in ((1, n) if n > 1 else (1,)):
+    env = dict(os.environ, PT_SEEDS="1,2,3,4", PT_GPUS=str(g), PT_SPP=spp, PT_MAX_TRIANGLES=str(1 << 20), PT_STATS="1", PT_TIMING="1")
     t0 = time.time()
     p = subprocess.run([exe, Wd, Ht], cwd=d, env=env, capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    print("".join(l + "\n" for l in p.stderr.splitlines() if l.startswith("PT_TIMING")), end="")
     raw = open(os.path.join(d, "result.ppm"), "rb").read()
     digests[g] = hashlib.sha256(raw).hexdigest()
     print("PT_GPUS=%d wall %.1f s |" % (g, time.time() - t0), re.search(r"Number of triangles: \d+", p.stdout).group(0), "|",
