@@ -25,11 +25,13 @@
  *   PT_STATS=1         append Mrays/s, samples/s and work counters after the reference's own lines
  */
 #define _GNU_SOURCE
+#include <dlfcn.h>
 #include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <unistd.h>
 
 #include "pthost.h"
 
@@ -49,8 +51,43 @@ static void tick(const char *what) {
 
 /* CUDA initialisation (1.3 s per device, 8 devices + the NCCL communicators several seconds) does not depend on the scene:
  * it runs on a helper thread while the main thread prints and parses triangles.txt. */
+/* The devices this process could see, WITHOUT initialising CUDA: the entries of CUDA_VISIBLE_DEVICES, or (unset) the NVML
+ * device count.  cuInit() on an 8-GPU NVSwitch box takes 5.5 s with all eight visible and 1.1 s with one (measured), so the
+ * drop-in narrows CUDA_VISIBLE_DEVICES to the devices it is going to use before the first CUDA call.  -1: unknown. */
+static int visible_devices(char entries[16][80]) {
+    const char *v = getenv("CUDA_VISIBLE_DEVICES");
+    int n = 0;
+    if (v && v[0]) {
+        while (*v && n < 16) {
+            size_t len = strcspn(v, ",");
+            if (len == 0 || len >= 80) return -1;
+            memcpy(entries[n], v, len);
+            entries[n][len] = 0;
+            ++n;
+            v += len;
+            if (*v == ',') ++v;
+        }
+        return *v ? -1 : n;
+    }
+    void *nvml = dlopen("libnvidia-ml.so.1", RTLD_NOW);
+    if (!nvml) return -1;
+    int (*init)(void) = (int (*)(void))dlsym(nvml, "nvmlInit_v2");
+    int (*count)(unsigned *) = (int (*)(unsigned *))dlsym(nvml, "nvmlDeviceGetCount_v2");
+    int (*shutdown)(void) = (int (*)(void))dlsym(nvml, "nvmlShutdown");
+    unsigned c = 0;
+    if (init && count && init() == 0) {
+        if (count(&c) != 0) c = 0;
+        if (shutdown) shutdown();
+    }
+    dlclose(nvml);
+    if (c == 0 || c > 16) return -1;
+    for (unsigned i = 0; i < c; ++i) snprintf(entries[i], 80, "%u", i);
+    return (int)c;
+}
+
 struct create_job {
     int ngpus;
+    int total_devices, public_dev;   /* what the reference's lines report: all visible devices, the index the user selected */
     int dev_count, dev, query_rc;
     char dev_name[256];
     int info_ready;
@@ -62,14 +99,19 @@ struct create_job {
 static void *create_worker(void *arg) {
     struct create_job *j = (struct create_job *)arg;
     int count = 0, dev = 0;
-    const int rc = pt_query_device(&count, &dev, j->dev_name, sizeof(j->dev_name));
+    int rc = pt_query_device(&count, &dev, j->dev_name, sizeof(j->dev_name));
+    if (j->total_devices > 0) {          /* CUDA_VISIBLE_DEVICES was narrowed: report the devices as the user sees them */
+        if (!rc && count < 1) rc = 1;
+        count = j->total_devices;
+        dev = j->public_dev;
+    }
     pthread_mutex_lock(&j->lock);
     j->dev_count = count; j->dev = dev; j->query_rc = rc; j->info_ready = 1;
     pthread_cond_signal(&j->cond);
     pthread_mutex_unlock(&j->lock);
     if (rc || dev < 0 || dev >= count) return NULL;            /* the main thread reports it, as select_device does */
     if (j->ngpus > 1) j->multi = pt_multi_create(j->ngpus);
-    else j->ctx = pt_create(dev);
+    else j->ctx = pt_create(j->total_devices > 0 ? 0 : dev);
     return NULL;
 }
 
@@ -108,6 +150,25 @@ int pth_cli_main(int variant, int argc, char **argv) {
     struct create_job job;
     memset(&job, 0, sizeof(job));
     job.ngpus = ngpus;
+    {
+        char entries[16][80];
+        const int total = visible_devices(entries);
+        const char *denv = getenv("PT_DEVICE");
+        if (!denv || !denv[0]) denv = getenv("OCL_DEVICE");
+        const int want = (denv && denv[0]) ? atoi(denv) : 0;
+        char narrowed[16 * 81] = "";
+        if (total > 1 && ngpus > 1 && ngpus < total) {
+            for (int i = 0; i < ngpus; ++i) { if (i) strcat(narrowed, ","); strcat(narrowed, entries[i]); }
+            job.total_devices = total; job.public_dev = want;
+        } else if (total > 1 && ngpus <= 1 && want >= 0 && want < total) {
+            strcpy(narrowed, entries[want]);
+            job.total_devices = total; job.public_dev = want;
+        }
+        if (narrowed[0]) {
+            setenv("CUDA_VISIBLE_DEVICES", narrowed, 1);
+            setenv("PT_DEVICE", "0", 1);                 /* inside the narrowed set */
+        }
+    }
     pthread_mutex_init(&job.lock, NULL);
     pthread_cond_init(&job.cond, NULL);
     pthread_t creator;
@@ -284,6 +345,13 @@ int pth_cli_main(int variant, int argc, char **argv) {
     pt_release_event(grid_evt);
     pt_release_event(light_evt);
     free(tris);
+    if (!getenv("PT_CLEAN_EXIT")) {
+        /* everything is written: leave without tearing the CUDA contexts and NCCL communicators down one by one (1.2 s of
+         * pt_multi_destroy plus ~2 s of driver teardown at 8 GPUs); the driver reclaims them with the process */
+        tick("done");
+        fflush(NULL);
+        _exit(0);
+    }
     if (multi) pt_multi_destroy(multi); else pt_destroy(ctx);
     tick("destroy");
     return 0;
