@@ -6,7 +6,7 @@ Layout:  csrc/ (CUDA kernels + C ABI + C host programs)   lib/ bin/ (built in-tr
 The drop-in boundary is the C ABI in include/ptcuda.h; see INTEGRATION.md.
 """
 from .api import (PtError, Renderer, RenderResult, Scene, camera, default_max_triangles, grid_dims, load_scene_dir,  # noqa: F401
-                  make_params, save_pam, load_pam, save_ppm, save_png, import_obj)
+                  make_params, save_pam, load_pam, save_ppm, save_png, import_obj, vlp_grid_dims)
 
 __all__ = ["PtError", "Renderer", "RenderResult", "Scene", "camera", "default_max_triangles", "grid_dims",
-           "load_scene_dir", "make_params", "save_pam", "load_pam", "save_ppm", "save_png", "import_obj"]
+           "load_scene_dir", "make_params", "save_pam", "load_pam", "save_ppm", "save_png", "import_obj", "vlp_grid_dims"]

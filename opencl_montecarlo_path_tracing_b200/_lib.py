@@ -144,6 +144,10 @@ PTCUDA_SYMBOLS = {
     "pt_probe_rng": (_I, [_VP, _U32P, C.c_uint32, _I, _FP, _U32P]),
     "pt_measure_peaks": (_I, [_VP, C.POINTER(C.c_double)]),
     "pt_last_kernel": (_I, [_VP]),
+    "pt_vlp_bounds": (_I, [_VP, _FP, _FP]),
+    "pt_build_vlp_grid": (_VP, [_VP, C.POINTER(pt_grid)]),
+    "pt_read_vlp_grid_csr": (_I, [_VP, _U32P, _U32P, C.POINTER(C.c_uint64)]),
+    "pt_read_vlp_grid_cells": (_I, [_VP, C.c_void_p, C.c_size_t]),
     "pt_query_device": (_I, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p, C.c_size_t]),
     "pt_debug_read_scratch": (_I, [_VP, C.c_void_p, C.c_size_t, C.c_size_t]),
 }

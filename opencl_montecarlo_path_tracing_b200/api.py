@@ -108,6 +108,16 @@ def grid_dims(scene, cell_size_modifier=3.0):
     return g
 
 
+def vlp_grid_dims(vmin, vmax, n_vlp, cell_size_modifier=3.0):
+    """Resolution / cell size of the VLP grid from its bounding box (CLSuperMetropolisPathTracer.c:628-636: the triangle
+    grid's formula with the VLP count)."""
+    g = pt_grid()
+    bmin = (C.c_float * 4)(*[float(v) for v in vmin])
+    bmax = (C.c_float * 4)(*[float(v) for v in vmax])
+    _lib.host_lib().pth_grid_dims(bmin, bmax, int(n_vlp), C.c_float(cell_size_modifier), C.byref(g))
+    return g
+
+
 def save_pam(path, image):
     img = np.ascontiguousarray(image, dtype=np.uint8)
     hgt, wid = img.shape[:2]
@@ -275,6 +285,41 @@ class Renderer:
         if self._l.pt_read_vpls(self.ctx, v.ctypes.data_as(C.POINTER(C.c_float)), max(n, 1)) < 0:
             raise PtError("pt_read_vpls failed: %s" % self._l.pt_last_error().decode())
         return v[:n]
+
+    # ---- VLP bounding box / VLP grid (CLSuperMetropolisPathTracer_vlpgrid) on the context's VLP buffer ----
+    def vlp_bounds(self):
+        """reduceMinAndMax_lmem(+_nwg): -> (vmin[4], vmax[4]) float32."""
+        lo, hi = (C.c_float * 4)(), (C.c_float * 4)()
+        _check(self._l.pt_vlp_bounds(self.ctx, lo, hi), "pt_vlp_bounds")
+        return np.array(lo[:], np.float32), np.array(hi[:], np.float32)
+
+    def build_vlp_grid(self, grid):
+        """initVLPsGrid on the VLP buffer; `grid` from vlp_grid_dims().  Returns the device time in ms."""
+        evt = self._l.pt_build_vlp_grid(self.ctx, C.byref(grid))
+        if not evt:
+            raise PtError("pt_build_vlp_grid failed: %s" % self._l.pt_last_error().decode())
+        ms = self._l.pt_runtime_ms(evt)
+        self._l.pt_release_event(evt)
+        self._vlp_grid = grid
+        return ms
+
+    def read_vlp_grid_csr(self):
+        total = C.c_uint64()
+        _check(self._l.pt_read_vlp_grid_csr(self.ctx, None, None, C.byref(total)), "pt_read_vlp_grid_csr")
+        g = self._vlp_grid
+        ncells = g.res[0] * g.res[1] * g.res[2]
+        start = np.zeros(ncells + 1, np.uint32)
+        refs = np.zeros(max(int(total.value), 1), np.uint32)
+        _check(self._l.pt_read_vlp_grid_csr(self.ctx, start.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                            refs.ctypes.data_as(C.POINTER(C.c_uint32)), None), "pt_read_vlp_grid_csr")
+        return start, refs[: int(total.value)]
+
+    def read_vlp_grid_cells(self):
+        g = self._vlp_grid
+        ncells = g.res[0] * g.res[1] * g.res[2]
+        raw = np.zeros(ncells * 128, np.uint8)
+        _check(self._l.pt_read_vlp_grid_cells(self.ctx, raw.ctypes.data_as(C.c_void_p), ncells), "pt_read_vlp_grid_cells")
+        return raw.reshape(ncells, 128)
 
     def render(self, variant, width, height, seeds, read_image=True, **kw):
         p = make_params(variant, width, height, seeds, **kw)

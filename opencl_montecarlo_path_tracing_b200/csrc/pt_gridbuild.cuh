@@ -13,6 +13,8 @@
 //               (e2, e0, v0 as 3 x float4), so a traversal step reads one dense block instead of
 //               chasing 16-bit indices into a triangle array.  32-bit ids: no 65536-triangle limit.
 #pragma once
+#include <float.h>
+
 #include "pt_host.h"
 
 namespace pt {
@@ -220,7 +222,180 @@ static int exclusive_scan(pt_ctx ctx, const uint32_t *in, size_t n, uint32_t cap
     return 0;
 }
 
+// ---- VLP bounding box and VLP grid of CLSuperMetropolisPathTracer_vlpgrid ------------------------------------------------
+// reduceMinAndMax_lmem / _nwg (metropolispathtracer.ocl:538-619) and initVLPsGrid (:621-647) are pure functions of a VLP
+// buffer (x y z intensity); a virtual point light with intensity 0 is a dummy and is ignored, every other one reaches
+// 16 sqrt(intensity) around its position.  Here: one reduction kernel (warp shuffles + one ordered atomic per block)
+// instead of two work-group tree passes — min / max do not depend on the order; NaN boxes never win, as in the reference's
+// isless / isgreater selects when they arrive from the partner lane — and the same deterministic count / scan / fill /
+// sort / emit as the triangle grid, so a cell lists its lights in ascending index order (the reference appends with
+// atomic_inc: any order; a serial run gives ascending).
+PT_DEV bool vlp_reach(float4 v, float lo[3], float hi[3]) {
+    if (v.w == 0.0f) return false;
+    const float r = __fmul_rn(16.0f, __fsqrt_rn(v.w));
+    lo[0] = __fsub_rn(v.x, r); lo[1] = __fsub_rn(v.y, r); lo[2] = __fsub_rn(v.z, r);
+    hi[0] = __fadd_rn(v.x, r); hi[1] = __fadd_rn(v.y, r); hi[2] = __fadd_rn(v.z, r);
+    return true;
+}
+
+// out[0..2] = keys of the minima, out[3..5] = keys of the maxima (ordered_key: monotone float -> uint)
+__global__ void k_vlp_bounds(const float4 *__restrict__ vpl, int n, unsigned *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {FLT_MIN, FLT_MIN, FLT_MIN};     // the reference's dummy box
+    if (i < n) {
+        float l[3], h[3];
+        if (vlp_reach(vpl[i], l, h))
+            for (int a = 0; a < 3; ++a) { if (l[a] == l[a]) lo[a] = l[a]; if (h[a] == h[a]) hi[a] = h[a]; }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        unsigned kmin = ordered_key(lo[a]), kmax = ordered_key(hi[a]);
+        kmin = __reduce_min_sync(0xffffffffu, kmin);
+        kmax = __reduce_max_sync(0xffffffffu, kmax);
+        if ((threadIdx.x & 31) == 0) { atomicMin(out + a, kmin); atomicMax(out + 3 + a, kmax); }
+    }
+}
+
+PT_DEV bool vlp_cell_range(float4 v, const GridDev &G, int lo[3], int hi[3]) {
+    float l[3], h[3];
+    if (!vlp_reach(v, l, h)) return false;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const int cl = f2i_rz_sat(__fdiv_rn(__fsub_rn(l[a], G.bmin[a]), G.cell[a]));
+        const int ch = f2i_rz_sat(__fdiv_rn(__fsub_rn(h[a], G.bmin[a]), G.cell[a]));
+        lo[a] = min(max(cl, 0), G.res[a] - 1);
+        hi[a] = min(max(ch, 0), G.res[a] - 1);
+    }
+    return true;
+}
+
+__global__ void k_vlp_count(const float4 *__restrict__ vpl, int n, GridDev G, uint32_t *__restrict__ count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int lo[3], hi[3];
+    if (!vlp_cell_range(vpl[i], G, lo, hi)) return;
+    for (int z = lo[2]; z <= hi[2]; ++z)
+        for (int y = lo[1]; y <= hi[1]; ++y)
+            for (int x = lo[0]; x <= hi[0]; ++x)
+                atomicAdd(&count[(size_t)z * G.res[0] * G.res[1] + (size_t)y * G.res[0] + x], 1u);
+}
+
+__global__ void k_vlp_fill(const float4 *__restrict__ vpl, int n, GridDev G, const uint32_t *__restrict__ start,
+                           uint32_t *__restrict__ cursor, uint32_t *__restrict__ refs) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int lo[3], hi[3];
+    if (!vlp_cell_range(vpl[i], G, lo, hi)) return;
+    for (int z = lo[2]; z <= hi[2]; ++z)
+        for (int y = lo[1]; y <= hi[1]; ++y)
+            for (int x = lo[0]; x <= hi[0]; ++x) {
+                size_t c = (size_t)z * G.res[0] * G.res[1] + (size_t)y * G.res[0] + x;
+                uint32_t pos = atomicAdd(&cursor[c], 1u);
+                refs[start[c] + pos] = (uint32_t)i;
+            }
+}
+
+// one thread per cell: ascending light indices, the first `cap` kept
+__global__ void k_vlp_emit(size_t ncells, uint32_t cap, const uint32_t *__restrict__ raw_start, uint32_t *__restrict__ raw_refs,
+                           const uint32_t *__restrict__ cap_start, uint32_t *__restrict__ refs) {
+    size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    uint32_t b = raw_start[c], e = raw_start[c + 1];
+    for (uint32_t i = b + 1; i < e; ++i) {
+        uint32_t key = raw_refs[i];
+        uint32_t j = i;
+        while (j > b && raw_refs[j - 1] > key) { raw_refs[j] = raw_refs[j - 1]; --j; }
+        raw_refs[j] = key;
+    }
+    uint32_t n = e - b;
+    if (n > cap) n = cap;
+    const uint32_t first = cap_start[c];
+    for (uint32_t k = 0; k < n; ++k) refs[first + k] = raw_refs[b + k];
+}
+
+static int grow_buf(void **ptr, size_t *capacity, size_t bytes, const char *what) {
+    if (*ptr && *capacity >= bytes) return 0;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr;
+    *capacity = 0;
+    PT_CUDA(cudaMalloc(ptr, bytes), what);
+    *capacity = bytes;
+    return 0;
+}
+
 }  // namespace pt
+
+// Bounding box of the context's VLP buffer (reduceMinAndMax_lmem + _nwg): vmin / vmax as the reference host reads them back
+int pt_vlp_bounds_device(pt_ctx ctx, float vmin[4], float vmax[4]) {
+    using namespace pt;
+    if (grow_buf((void **)&ctx->d_vlp_keys, &ctx->vlp_keys_cap, 6 * sizeof(unsigned), "alloc VLP bounds")) return 1;
+    unsigned init[6], keys[6];
+    {
+        const float fmx = FLT_MAX, fmn = FLT_MIN;
+        unsigned u;
+        memcpy(&u, &fmx, 4); init[0] = init[1] = init[2] = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+        memcpy(&u, &fmn, 4); init[3] = init[4] = init[5] = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    }
+    PT_CUDA(cudaMemcpyAsync(ctx->d_vlp_keys, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream), "init VLP bounds");
+    if (ctx->nvpl > 0) {
+        k_vlp_bounds<<<(ctx->nvpl + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_vpls, ctx->nvpl, ctx->d_vlp_keys);
+        PT_CUDA(cudaGetLastError(), "VLP bounds");
+    }
+    PT_CUDA(cudaMemcpyAsync(keys, ctx->d_vlp_keys, sizeof(keys), cudaMemcpyDeviceToHost, ctx->stream), "read VLP bounds");
+    PT_CUDA(cudaStreamSynchronize(ctx->stream), "sync VLP bounds");
+    for (int a = 0; a < 6; ++a) {
+        const unsigned k = keys[a], u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+        float f;
+        memcpy(&f, &u, 4);
+        (a < 3 ? vmin : vmax)[a % 3] = f;
+    }
+    vmin[3] = vmax[3] = 0.0f;
+    return 0;
+}
+
+// initVLPsGrid on the context's VLP buffer: capped CSR (cell -> first ref, refs = light indices, ascending per cell)
+int pt_vlp_grid_build_device(pt_ctx ctx, const pt_grid *g) {
+    using namespace pt;
+    const size_t ncells = (size_t)g->res[0] * g->res[1] * g->res[2];
+    const uint32_t cap = g->max_refs_per_cell > 0 ? (uint32_t)g->max_refs_per_cell : 62u;
+    const int n = ctx->nvpl;
+    GridDev G;
+    for (int a = 0; a < 3; ++a) { G.bmin[a] = g->box_min[a]; G.bmax[a] = g->box_max[a]; G.cell[a] = g->cell_size[a]; G.res[a] = g->res[a]; }
+    G.cells = nullptr; G.recs = nullptr; G.sph = nullptr; G.sph_k = INFINITY;
+    const int nblocks = (int)((ncells + SCAN_BLOCK - 1) / SCAN_BLOCK);
+    if (grow_buf((void **)&ctx->gb_count, &ctx->gb_cap[0], ncells * 4, "alloc grid count")) return 1;
+    if (grow_buf((void **)&ctx->gb_raw_start, &ctx->gb_cap[1], (ncells + 1) * 4, "alloc grid start")) return 1;
+    if (grow_buf((void **)&ctx->gb_cursor, &ctx->gb_cap[2], ncells * 4, "alloc grid cursor")) return 1;
+    if (grow_buf((void **)&ctx->gb_bsums, &ctx->gb_cap[3], (size_t)(nblocks + 1) * 4, "alloc scan sums")) return 1;
+    if (grow_buf((void **)&ctx->d_vlp_cell_start, &ctx->vlp_start_cap, (ncells + 1) * 4, "alloc VLP cell_start")) return 1;
+    PT_CUDA(cudaMemsetAsync(ctx->gb_count, 0, ncells * 4, ctx->stream), "memset");
+    PT_CUDA(cudaMemsetAsync(ctx->gb_cursor, 0, ncells * 4, ctx->stream), "memset");
+    const int tb = 256, tg = (n + tb - 1) / tb;
+    if (n > 0) {
+        k_vlp_count<<<tg, tb, 0, ctx->stream>>>(ctx->d_vpls, n, G, ctx->gb_count);
+        PT_CUDA(cudaGetLastError(), "VLP grid count");
+    }
+    if (exclusive_scan(ctx, ctx->gb_count, ncells, 0, ctx->gb_raw_start, ctx->gb_bsums)) return 1;
+    if (exclusive_scan(ctx, ctx->gb_count, ncells, cap, ctx->d_vlp_cell_start, ctx->gb_bsums)) return 1;
+    uint32_t raw_total = 0, cap_total = 0;
+    PT_CUDA(cudaMemcpyAsync(&raw_total, ctx->gb_raw_start + ncells, 4, cudaMemcpyDeviceToHost, ctx->stream), "read total");
+    PT_CUDA(cudaMemcpyAsync(&cap_total, ctx->d_vlp_cell_start + ncells, 4, cudaMemcpyDeviceToHost, ctx->stream), "read total");
+    PT_CUDA(cudaStreamSynchronize(ctx->stream), "sync VLP grid totals");
+    if (grow_buf((void **)&ctx->gb_raw_refs, &ctx->gb_cap[6], (size_t)(raw_total ? raw_total : 1) * 4, "alloc raw refs")) return 1;
+    if (grow_buf((void **)&ctx->d_vlp_refs, &ctx->vlp_refs_cap, (size_t)(cap_total ? cap_total : 1) * 4, "alloc VLP refs")) return 1;
+    if (n > 0) {
+        k_vlp_fill<<<tg, tb, 0, ctx->stream>>>(ctx->d_vpls, n, G, ctx->gb_raw_start, ctx->gb_cursor, ctx->gb_raw_refs);
+        PT_CUDA(cudaGetLastError(), "VLP grid fill");
+    }
+    k_vlp_emit<<<(unsigned)((ncells + 127) / 128), 128, 0, ctx->stream>>>(ncells, cap, ctx->gb_raw_start, ctx->gb_raw_refs,
+                                                                       ctx->d_vlp_cell_start, ctx->d_vlp_refs);
+    PT_CUDA(cudaGetLastError(), "VLP grid emit");
+    ctx->vlp_grid_desc = *g;
+    ctx->vlp_ncells = ncells;
+    ctx->vlp_total_refs = cap_total;
+    ctx->vlp_grid_set = true;
+    return 0;
+}
 
 int pt_grid_build_device(pt_ctx ctx, const pt_grid *g) {
     using namespace pt;

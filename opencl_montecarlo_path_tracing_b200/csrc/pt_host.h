@@ -81,6 +81,14 @@ struct pt_ctx_s {
     uint32_t *gb_count, *gb_raw_start, *gb_cursor, *gb_bsums, *gb_raw_refs;   // build scratch, kept between builds
     size_t gb_cap[11];            // capacities (bytes) of the five scratch buffers, cell_start, cells, refs, recs
 
+    // VLP grid of CLSuperMetropolisPathTracer_vlpgrid on the context's VLP buffer (pt_build_vlp_grid)
+    bool vlp_grid_set;
+    pt_grid vlp_grid_desc;
+    unsigned *d_vlp_keys;
+    uint32_t *d_vlp_cell_start, *d_vlp_refs;
+    size_t vlp_keys_cap, vlp_start_cap, vlp_refs_cap, vlp_ncells;
+    uint64_t vlp_total_refs;
+
     // render targets owned by the context
     uint32_t *d_rgba;
     float4 *d_accum;
@@ -147,6 +155,8 @@ int pt_launch_persistent(pt_ctx ctx, const pt_render_params *p, const pt::Launch
 int pt_launch_wavefront(pt_ctx ctx, const pt_render_params *p, const pt::LaunchArgs &args);
 int pt_launch_grid_tma(pt_ctx ctx, const pt_render_params *p, const pt::LaunchArgs &args);
 int pt_grid_build_device(pt_ctx ctx, const pt_grid *g);
+int pt_vlp_bounds_device(pt_ctx ctx, float vmin[4], float vmax[4]);
+int pt_vlp_grid_build_device(pt_ctx ctx, const pt_grid *g);
 int pt_launch_stream_grid(pt_ctx ctx, const pt_render_params *p, const pt::LaunchArgs &args);
 int pt_launch_spec(pt_ctx ctx, const pt_render_params *p, const pt::LaunchArgs &args);
 int pt_launch_grid_pool(pt_ctx ctx, const pt_render_params *p, const pt::LaunchArgs &args);

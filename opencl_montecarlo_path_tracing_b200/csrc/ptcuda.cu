@@ -177,6 +177,7 @@ extern "C" void pt_destroy(pt_ctx c) {
     if (c->h_tile_order) cudaFreeHost(c->h_tile_order);
     if (c->h_cta_times) cudaFreeHost(c->h_cta_times);
     cudaFree(c->d_vpls); cudaFree(c->d_vpl_active); cudaFree(c->d_vpl_count);
+    cudaFree(c->d_vlp_keys); cudaFree(c->d_vlp_cell_start); cudaFree(c->d_vlp_refs);
     if (c->wf_exec) cudaGraphExecDestroy(c->wf_exec);
     free(c->wf_key_args);
     if (c->h_rgba) cudaFreeHost(c->h_rgba);
@@ -461,6 +462,66 @@ extern "C" int pt_read_grid_cells(pt_ctx c, void *cells, size_t ncells) {
     uint32_t *start = (uint32_t *)malloc((ncells + 1) * 4);
     uint32_t *refs = (uint32_t *)malloc((c->total_refs ? c->total_refs : 1) * 4);
     int rc = pt_read_grid_csr(c, start, refs, nullptr);
+    if (!rc) {
+        unsigned char *out = (unsigned char *)cells;
+        memset(out, 0, ncells * 128);
+        for (size_t i = 0; i < ncells; ++i) {
+            uint32_t n = start[i + 1] - start[i];
+            if (n > 62) n = 62;
+            memcpy(out + 128 * i, &n, 4);
+            for (uint32_t k = 0; k < n; ++k) {
+                uint16_t id = (uint16_t)refs[start[i] + k];
+                memcpy(out + 128 * i + 4 + 2 * k, &id, 2);
+            }
+        }
+    }
+    free(start);
+    free(refs);
+    return rc;
+}
+
+// ---------------------------------------------------------------- VLP bounding box / VLP grid (CLSuperMetropolisPathTracer_vlpgrid)
+extern "C" int pt_vlp_bounds(pt_ctx c, float vmin[4], float vmax[4]) {
+    if (!c || !vmin || !vmax) return pt_fail(1, "pt_vlp_bounds: null argument");
+    if (!c->vpls_set) return pt_fail(1, "pt_vlp_bounds: no VLP buffer (pt_launch_lighttracer or pt_set_vpls first)");
+    PT_CUDA(cudaSetDevice(c->device), "select device");
+    return pt_vlp_bounds_device(c, vmin, vmax);
+}
+
+extern "C" pt_event pt_build_vlp_grid(pt_ctx c, const pt_grid *g) {
+    if (!c || !g) { pt_fail(1, "pt_build_vlp_grid: null argument"); return nullptr; }
+    if (!c->vpls_set) { pt_fail(1, "pt_build_vlp_grid: no VLP buffer (pt_launch_lighttracer or pt_set_vpls first)"); return nullptr; }
+    if (g->res[0] < 1 || g->res[1] < 1 || g->res[2] < 1 || (long long)g->res[0] * g->res[1] * g->res[2] > (1ll << 28)) {
+        pt_fail(1, "pt_build_vlp_grid: bad resolution %d x %d x %d", g->res[0], g->res[1], g->res[2]);
+        return nullptr;
+    }
+    PT_CUDA_NULL(cudaSetDevice(c->device), "select device");
+    pt_event e = event_new(c);
+    if (!e) return nullptr;
+    cudaEventRecord(e->start, c->stream);
+    if (pt_vlp_grid_build_device(c, g)) { pt_release_event(e); return nullptr; }
+    cudaEventRecord(e->stop, c->stream);
+    return e;
+}
+
+extern "C" int pt_read_vlp_grid_csr(pt_ctx c, uint32_t *cell_start, uint32_t *refs, uint64_t *total_refs) {
+    if (!c || !c->vlp_grid_set) return pt_fail(1, "pt_read_vlp_grid_csr: no VLP grid built");
+    if (total_refs) *total_refs = c->vlp_total_refs;
+    PT_CUDA(cudaSetDevice(c->device), "select device");
+    if (cell_start) PT_CUDA(cudaMemcpyAsync(cell_start, c->d_vlp_cell_start, (c->vlp_ncells + 1) * 4, cudaMemcpyDeviceToHost, c->stream), "read VLP cell_start");
+    if (refs && c->vlp_total_refs) PT_CUDA(cudaMemcpyAsync(refs, c->d_vlp_refs, c->vlp_total_refs * 4, cudaMemcpyDeviceToHost, c->stream), "read VLP refs");
+    PT_CUDA(cudaStreamSynchronize(c->stream), "sync VLP grid read");
+    return 0;
+}
+
+// the reference's 128-byte Cell {uint nels; ushort elem_index[62]} (metropolispathtracer.ocl Cell, host .c:39-42)
+extern "C" int pt_read_vlp_grid_cells(pt_ctx c, void *cells, size_t ncells) {
+    if (!c || !c->vlp_grid_set) return pt_fail(1, "pt_read_vlp_grid_cells: no VLP grid built");
+    if (ncells != c->vlp_ncells) return pt_fail(1, "pt_read_vlp_grid_cells: expected %zu cells", c->vlp_ncells);
+    if (c->nvpl > 65536) return pt_fail(1, "pt_read_vlp_grid_cells: 16-bit cell format needs <= 65536 VLPs");
+    uint32_t *start = (uint32_t *)malloc((ncells + 1) * 4);
+    uint32_t *refs = (uint32_t *)malloc((c->vlp_total_refs ? c->vlp_total_refs : 1) * 4);
+    int rc = pt_read_vlp_grid_csr(c, start, refs, nullptr);
     if (!rc) {
         unsigned char *out = (unsigned char *)cells;
         memset(out, 0, ncells * 128);

@@ -123,6 +123,12 @@ void oracle_grid_dims(const float box_min[4], const float box_max[4], int ntrian
  * ncells+1 offsets.  Returns total refs stored. */
 uint64_t oracle_build_grid(const float *tris12, int ntris, const float box_min[4], const int32_t grid_res[4],
                            const float cell_size[4], int cap, uint32_t *cell_start, uint32_t *cell_refs);
+/* CLSuperMetropolisPathTracer_vlpgrid: VLP bounding box (kernels reduceMinAndMax_lmem + _nwg, metropolispathtracer.ocl:538-619)
+ * and VLP grid (kernel initVLPsGrid, :621-647; ascending light indices per cell, at most `cap`).  The grid's resolution is
+ * oracle_grid_dims(vmin, vmax, n_vlp, modifier) (CLSuperMetropolisPathTracer.c:628-636). */
+void oracle_vlp_bounds(const float *vpl4, int n, float vmin[4], float vmax[4]);
+uint64_t oracle_build_vlp_grid(const float *vpl4, int n, const float box_min[4], const int32_t grid_res[4], const float cell_size[4],
+                               int cap, uint32_t *cell_start, uint32_t *cell_refs);
 /* pamalign.h:212-238 */
 int oracle_save_pam(const char *path, int width, int height, const uint8_t *rgba8);
 

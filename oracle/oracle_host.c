@@ -176,6 +176,82 @@ uint64_t oracle_build_grid(const float *tris12, int ntris, const float box_min[4
     return total;
 }
 
+/* ---- VLP bounding box and VLP grid of CLSuperMetropolisPathTracer_vlpgrid --------------------------------------------
+ * kernels reduceMinAndMax_lmem / reduceMinAndMax_lmem_nwg (metropolispathtracer.ocl:538-619): a light (x y z intensity)
+ * with intensity 0 is a dummy (box FLT_MAX / FLT_MIN), every other one spans position -+ 16 * sqrt(intensity); the two
+ * tree passes keep, per component, the smaller minimum / larger maximum (isless / isgreater + select: a NaN arriving
+ * from the partner never wins; restated as "NaN components are skipped").  vmin / vmax as the host reads the Box back
+ * (CLSuperMetropolisPathTracer.c:606-611). */
+static int vlp_reach(const float *v, float lo[3], float hi[3]) {
+    if (v[3] == 0.0f) return 0;
+    volatile float r = 16.0f * sqrtf(v[3]);
+    for (int a = 0; a < 3; ++a) {
+        volatile float l = v[a] - r, h = v[a] + r;
+        lo[a] = l; hi[a] = h;
+    }
+    return 1;
+}
+
+void oracle_vlp_bounds(const float *vpl4, int n, float vmin[4], float vmax[4]) {
+    for (int a = 0; a < 3; ++a) { vmin[a] = FLT_MAX; vmax[a] = FLT_MIN; }
+    vmin[3] = vmax[3] = 0.0f;
+    for (int i = 0; i < n; ++i) {
+        float lo[3], hi[3];
+        if (!vlp_reach(vpl4 + 4 * (size_t)i, lo, hi)) continue;
+        for (int a = 0; a < 3; ++a) {
+            if (lo[a] < vmin[a]) vmin[a] = lo[a];
+            if (hi[a] > vmax[a]) vmax[a] = hi[a];
+        }
+    }
+}
+
+/* kernel initVLPsGrid (metropolispathtracer.ocl:621-647): cell range = clamp(convert_int4(((pos -+ r) - boxmin) / cell_size),
+ * 0, res - 1); every overlapped cell gets the light's index, at most `cap` (62) per cell.  The reference appends with
+ * atomic_inc (any order); here ascending index order, what a serial run of the kernel produces. */
+static void vlp_cell_range(const float *v, const float box_min[4], const int32_t res[4], const float cell[4], int lo[3], int hi[3], int *live) {
+    float l[3], h[3];
+    *live = vlp_reach(v, l, h);
+    if (!*live) return;
+    for (int a = 0; a < 3; ++a) {
+        volatile float dl = l[a] - box_min[a], dh = h[a] - box_min[a];
+        volatile float ql = dl / cell[a], qh = dh / cell[a];
+        int cl = f2i_rz_sat(ql), ch = f2i_rz_sat(qh);
+        lo[a] = cl < 0 ? 0 : (cl > res[a] - 1 ? res[a] - 1 : cl);
+        hi[a] = ch < 0 ? 0 : (ch > res[a] - 1 ? res[a] - 1 : ch);
+    }
+}
+
+uint64_t oracle_build_vlp_grid(const float *vpl4, int n, const float box_min[4], const int32_t grid_res[4], const float cell_size[4],
+                               int cap, uint32_t *cell_start, uint32_t *cell_refs) {
+    size_t ncells = (size_t)grid_res[0] * grid_res[1] * grid_res[2];
+    uint32_t *count = (uint32_t *)calloc(ncells + 1, sizeof(uint32_t));
+    int lo[3], hi[3], live;
+    for (int pass = 0; pass < (cell_refs ? 2 : 1); ++pass) {
+        if (pass == 1) memset(count, 0, (ncells + 1) * sizeof(uint32_t));
+        for (int i = 0; i < n; ++i) {
+            vlp_cell_range(vpl4 + 4 * (size_t)i, box_min, grid_res, cell_size, lo, hi, &live);
+            if (!live) continue;
+            for (int z = lo[2]; z <= hi[2]; ++z)
+                for (int y = lo[1]; y <= hi[1]; ++y)
+                    for (int x = lo[0]; x <= hi[0]; ++x) {
+                        size_t c = (size_t)z * grid_res[0] * grid_res[1] + (size_t)y * grid_res[0] + x;
+                        if ((int)count[c] < cap) {
+                            if (pass == 1) cell_refs[cell_start[c] + count[c]] = (uint32_t)i;
+                            count[c]++;
+                        }
+                    }
+        }
+        if (pass == 0) {
+            uint64_t total = 0;
+            for (size_t c = 0; c < ncells; ++c) { cell_start[c] = (uint32_t)total; total += count[c]; }
+            cell_start[ncells] = (uint32_t)total;
+        }
+    }
+    uint64_t total = cell_start[ncells];
+    free(count);
+    return total;
+}
+
 /* pamalign.h:212-238: "P7" header + raw RGBA bytes */
 int oracle_save_pam(const char *path, int width, int height, const uint8_t *rgba8) {
     FILE *f = fopen(path, "wb");

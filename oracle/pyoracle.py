@@ -130,6 +130,24 @@ class OracleLib:
         self.lib.oracle_build_grid(*a, start.ctypes.data_as(C.c_void_p), refs.ctypes.data_as(C.c_void_p))
         return start, refs[: int(total)]
 
+    def vlp_bounds(self, vpl):
+        vpl = np.ascontiguousarray(vpl, np.float32).reshape(-1, 4)
+        lo, hi = (C.c_float * 4)(), (C.c_float * 4)()
+        self.lib.oracle_vlp_bounds(vpl.ctypes.data_as(C.c_void_p), C.c_int(vpl.shape[0]), lo, hi)
+        return np.array(lo[:], np.float32), np.array(hi[:], np.float32)
+
+    def build_vlp_grid(self, vpl, box_min, res, cell, cap=62):
+        vpl = np.ascontiguousarray(vpl, np.float32).reshape(-1, 4)
+        ncells = int(res[0]) * int(res[1]) * int(res[2])
+        start = np.zeros(ncells + 1, np.uint32)
+        a = (vpl.ctypes.data_as(C.c_void_p), C.c_int(vpl.shape[0]), (C.c_float * 4)(*box_min), (C.c_int32 * 4)(*[int(x) for x in res]),
+             (C.c_float * 4)(*cell), C.c_int(cap))
+        self.lib.oracle_build_vlp_grid.restype = C.c_uint64
+        total = self.lib.oracle_build_vlp_grid(*a, start.ctypes.data_as(C.c_void_p), None)
+        refs = np.zeros(max(int(total), 1), np.uint32)
+        self.lib.oracle_build_vlp_grid(*a, start.ctypes.data_as(C.c_void_p), refs.ctypes.data_as(C.c_void_p))
+        return start, refs[: int(total)]
+
     def save_pam(self, path, image):
         img = np.ascontiguousarray(image, np.uint8)
         return self.lib.oracle_save_pam(path.encode(), img.shape[1], img.shape[0], img.ctypes.data_as(C.c_void_p))

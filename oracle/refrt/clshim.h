@@ -25,6 +25,7 @@
 #ifndef REFRT_CLSHIM_H
 #define REFRT_CLSHIM_H
 
+#include <cfloat>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -81,6 +82,10 @@ struct alignas(sizeof(T) * 4) vec4 {
     explicit vec4(A a) { x = (T)a; y = (T)a; z = (T)a; w = (T)a; }
 };
 
+/* 8- and 16-component float vectors: only what the VLP-grid kernels of CLSuperMetropolisPathTracer_vlpgrid use —
+ * (float8)(lo, hi), .lo / .hi, whole-vector loads and stores */
+struct alignas(64) float16 { float v[16]; };
+
 typedef vec2<float> float2;
 typedef vec2<uint>  uint2;
 typedef vec2<int>   int2;
@@ -88,6 +93,13 @@ typedef vec4<float> float4;
 typedef vec4<int>   int4;
 typedef vec4<uint>  uint4;
 typedef vec4<uchar> uchar4;
+
+/* float8 as a pair of float4 (defined after float4 is complete) */
+struct alignas(32) float8 {
+    float4 lo, hi;
+    float8() = default;
+    float8(float4 a, float4 b) { lo = a; hi = b; }
+};
 
 #define REFRT_BINOP(OP)                                                                            \
     template <class T> inline vec4<T> operator OP(vec4<T> a, vec4<T> b) {                          \
@@ -152,6 +164,8 @@ inline uchar4 convert_uchar4(float4 a) {
 /* --------------------------------------------------------------------- math */
 inline float sqrt(float x) { return ::sqrtf(x); }
 inline float fabs(float x) { return ::fabsf(x); }
+inline float4 fabs(float4 a) { return float4(::fabsf(a.x), ::fabsf(a.y), ::fabsf(a.z), ::fabsf(a.w)); }
+inline float floor(float x) { return ::floorf(x); }
 inline float ceil(float x) { return ::ceilf(x); }
 template <class E, class = typename std::enable_if<is_scalar<E>::value>::type>
 inline float pow(float x, E e) { return ::powf(x, (float)e); }
@@ -188,6 +202,8 @@ inline int4 isgreaterequal(float4 a, S b) {
     float f = (float)b;
     return int4(a.x >= f ? -1 : 0, a.y >= f ? -1 : 0, a.z >= f ? -1 : 0, a.w >= f ? -1 : 0);
 }
+inline int4 isless(float4 a, float4 b) { return int4(a.x < b.x ? -1 : 0, a.y < b.y ? -1 : 0, a.z < b.z ? -1 : 0, a.w < b.w ? -1 : 0); }
+inline int4 isgreater(float4 a, float4 b) { return int4(a.x > b.x ? -1 : 0, a.y > b.y ? -1 : 0, a.z > b.z ? -1 : 0, a.w > b.w ? -1 : 0); }
 /* select(a, b, c): per lane, MSB(c) ? b : a */
 template <class T> inline vec4<T> select(vec4<T> a, vec4<T> b, int4 c) {
     return vec4<T>(c.x < 0 ? b.x : a.x, c.y < 0 ? b.y : a.y, c.z < 0 ? b.z : a.z, c.w < 0 ? b.w : a.w);

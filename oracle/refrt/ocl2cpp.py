@@ -16,7 +16,7 @@ rewrite would let g++ evaluate them right-to-left.
 import re
 import sys
 
-VEC_TYPES = ("float2", "float4", "uint2", "uint4", "int2", "int4", "uchar4")
+VEC_TYPES = ("float2", "float4", "float8", "uint2", "uint4", "int2", "int4", "uchar4")
 PAT = re.compile(r"\(\s*(" + "|".join(VEC_TYPES) + r")\s*\)\s*\(")
 
 

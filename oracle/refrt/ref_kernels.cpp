@@ -8,6 +8,7 @@
  *   REF_VARIANT 2  CLSuperPathTracer_lmem_NoDoF/pathtracer.ocl   (nodof)
  *   REF_VARIANT 3  CLSuperPathTracer_trianglegrid/pathtracer.ocl (grid)
  *   REF_VARIANT 4  CLSuperBidirectionalPathTracer/bidirectionalpathtracer.ocl (bidir)
+ *   REF_VARIANT 5  CLSuperMetropolisPathTracer_vlpgrid/metropolispathtracer.ocl (VLP bounding box + VLP grid kernels only)
  *
  * REF_OCL_GEN is the reference source with vector literals rewritten by ocl2cpp.py; the Makefile
  * pipes it in ("/dev/stdin"), so no copy of it is written anywhere.  Argument
@@ -110,8 +111,25 @@ static void tramp_lightTracer(const RefLaunch &L) {
 }
 const RefKernelDesc ref_kernel_table[] = {
     {"pathTracer", 18, tramp_pathTracer}, {"lightTracer", 12, tramp_lightTracer}, {nullptr, 0, nullptr}};
+#elif REF_VARIANT == 5
+/* CLSuperMetropolisPathTracer_vlpgrid/metropolispathtracer.ocl: only the kernels that are pure functions of a VLP buffer
+ * are registered (argument order: CLSuperMetropolisPathTracer.c:262-296 reduction(), :298-321 initVLPsGrid()); the
+ * Metropolis light tracer and the path tracer of that program are compiled but not exposed. */
+static void tramp_reduce_minmax(const RefLaunch &L) {
+    ocl::reduceMinAndMax_lmem((float4 *)L.mem(0), (float8 *)L.mem(1), (float8 *)L.local(2), L.val<int>(3));
+}
+static void tramp_reduce_minmax_nwg(const RefLaunch &L) {
+    ocl::reduceMinAndMax_lmem_nwg((float8 *)L.mem(0), (float8 *)L.mem(1), (float8 *)L.local(2), L.val<int>(3));
+}
+static void tramp_init_vlps_grid(const RefLaunch &L) {
+    ocl::initVLPsGrid((Cell *)L.mem(0), (const float4 *)L.mem(1), L.val<float4>(2), L.val<int4>(3), L.val<float4>(4));
+}
+const RefKernelDesc ref_kernel_table[] = {{"reduceMinAndMax_lmem", 4, tramp_reduce_minmax},
+                                          {"reduceMinAndMax_lmem_nwg", 4, tramp_reduce_minmax_nwg},
+                                          {"initVLPsGrid", 5, tramp_init_vlps_grid},
+                                          {nullptr, 0, nullptr}};
 #else
-#error "REF_VARIANT must be 0..4"
+#error "REF_VARIANT must be 0..5"
 #endif
 
 /* ------------------------------------------------------------------ probes */

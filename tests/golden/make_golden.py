@@ -236,6 +236,75 @@ def bidir_golden(tmp):
     np.savez_compressed(os.path.join(HERE, "golden_bidir.npz"), **out)
 
 
+def vlpgrid_golden(tmp):
+    """VLP bounding box (reduceMinAndMax_lmem + _nwg) and VLP grid (initVLPsGrid) of CLSuperMetropolisPathTracer_vlpgrid, run
+    by the reference's own kernels (libref_vlpgrid.so through refrt's CL entry points, launched as its host does:
+    CLSuperMetropolisPathTracer.c:262-296, 298-321, 586-647) on injected VLP buffers."""
+    from oracle.pyoracle import OracleLib
+    o = OracleLib(0)
+    d = os.path.join(tmp, "vlp_bidir")
+    write_scenes.write_variant("bidir", d)
+    sc = o.load_scene_dir(d, "bidir")
+    rng = np.random.default_rng(20261018)
+    synth = np.zeros((3000, 4), np.float32)
+    synth[:, :3] = rng.uniform(-5, 30, (3000, 3))
+    synth[:, 3] = rng.uniform(0, 0.02, 3000) ** 2 * 50
+    synth[rng.random(3000) < 0.3, 3] = 0.0                         # dummy lights
+    few = np.array([[1, 2, 3, 0.25], [0, 0, 0, 0], [4, 1, 0.5, 0.01]], np.float32)
+    buffers = {"bidir": ref_light_tracer(lib("bidir"), sc, SEED_SETS[0], 512), "synthetic": synth, "few": few,
+               "all_dummy": np.zeros((300, 4), np.float32)}
+    L = lib("vlpgrid")
+    for fn in ("clCreateKernel", "clCreateBuffer", "clEnqueueMapBuffer"):
+        getattr(L, fn).restype = C.c_void_p
+    err = C.c_int()
+    out = {}
+    for name, vpl in buffers.items():
+        vpl = np.ascontiguousarray(vpl, np.float32).reshape(-1, 4)
+        n = vpl.shape[0]
+        lws = 256
+        nwg = (n + lws - 1) // lws
+        box = np.zeros(max(nwg, 1) * 8, np.float32)
+        b1 = C.c_void_p(L.clCreateBuffer(None, C.c_uint64(1 << 5), C.c_size_t(vpl.nbytes), vpl.ctypes.data_as(C.c_void_p), C.byref(err)))
+        b2 = C.c_void_p(L.clCreateBuffer(None, C.c_uint64(1 << 5), C.c_size_t(box.nbytes), box.ctypes.data_as(C.c_void_p), C.byref(err)))
+        nn = C.c_int(n)
+        k = C.c_void_p(L.clCreateKernel(None, b"reduceMinAndMax_lmem", C.byref(err)))
+        L.clSetKernelArg(k, 0, C.c_size_t(8), C.byref(b1)); L.clSetKernelArg(k, 1, C.c_size_t(8), C.byref(b2))
+        L.clSetKernelArg(k, 2, C.c_size_t(32 * lws), None); L.clSetKernelArg(k, 3, C.c_size_t(4), C.byref(nn))
+        assert L.clEnqueueNDRangeKernel(None, k, 1, None, (C.c_size_t * 1)(nwg * lws), (C.c_size_t * 1)(lws), 0, None, None) == 0
+        if nwg > 1:
+            k2 = C.c_void_p(L.clCreateKernel(None, b"reduceMinAndMax_lmem_nwg", C.byref(err)))
+            nw = C.c_int(nwg)
+            L.clSetKernelArg(k2, 0, C.c_size_t(8), C.byref(b2)); L.clSetKernelArg(k2, 1, C.c_size_t(8), C.byref(b2))
+            L.clSetKernelArg(k2, 2, C.c_size_t(32 * lws), None); L.clSetKernelArg(k2, 3, C.c_size_t(4), C.byref(nw))
+            assert L.clEnqueueNDRangeKernel(None, k2, 1, None, (C.c_size_t * 1)(lws), (C.c_size_t * 1)(lws), 0, None, None) == 0
+        ptr = L.clEnqueueMapBuffer(None, b2, 1, 1, C.c_size_t(0), C.c_size_t(32), 0, None, None, C.byref(err))
+        bb = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=(8,)).copy()
+        vmin, vmax = bb[:4].copy(), bb[4:].copy()
+        out[name + "_vpl"] = vpl.view(np.uint32)
+        out[name + "_vmin"] = vmin.view(np.uint32); out[name + "_vmax"] = vmax.view(np.uint32)
+        if name == "all_dummy":
+            continue                                               # FLT_MAX / FLT_MIN box: the host's grid formula is meaningless
+        res, cell = o.grid_dims(vmin, vmax, n, 3.0)
+        ncells = int(res[0] * res[1] * res[2])
+        cells = np.zeros(ncells * 128, np.uint8)
+        bc = C.c_void_p(L.clCreateBuffer(None, C.c_uint64(1 << 5), C.c_size_t(cells.nbytes), cells.ctypes.data_as(C.c_void_p), C.byref(err)))
+        kg = C.c_void_p(L.clCreateKernel(None, b"initVLPsGrid", C.byref(err)))
+        v4 = (C.c_float * 4)(*vmin); r4 = (C.c_int32 * 4)(*[int(x) for x in res]); c4 = (C.c_float * 4)(*cell)
+        L.clSetKernelArg(kg, 0, C.c_size_t(8), C.byref(bc)); L.clSetKernelArg(kg, 1, C.c_size_t(8), C.byref(b1))
+        L.clSetKernelArg(kg, 2, C.c_size_t(16), v4); L.clSetKernelArg(kg, 3, C.c_size_t(16), r4); L.clSetKernelArg(kg, 4, C.c_size_t(16), c4)
+        assert L.clEnqueueNDRangeKernel(None, kg, 1, None, (C.c_size_t * 1)(n), None, 0, None, None) == 0
+        ptr = L.clEnqueueMapBuffer(None, bc, 1, 1, C.c_size_t(0), C.c_size_t(cells.nbytes), 0, None, None, C.byref(err))
+        got = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(ncells, 128)).copy()
+        nels = got[:, :4].copy().view(np.uint32).reshape(-1)
+        ids = got[:, 4:].copy().view(np.uint16).reshape(ncells, 62)
+        srt = np.full((ncells, 62), 65535, np.uint16)              # atomic_inc order is arbitrary: ids stored sorted
+        for c in range(ncells):
+            m = min(int(nels[c]), 62)
+            srt[c, :m] = np.sort(ids[c, :m])
+        out[name + "_res"] = res; out[name + "_cell"] = cell.view(np.uint32); out[name + "_nels"] = nels; out[name + "_ids"] = srt
+    np.savez_compressed(os.path.join(HERE, "golden_vlpgrid.npz"), **out)
+
+
 if __name__ == "__main__":
     sys.path.insert(0, ROOT)
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref", "oracle"])
@@ -243,9 +312,13 @@ if __name__ == "__main__":
         if sys.argv[1:] == ["bidir"]:
             bidir_golden(tmp)
             sys.exit(0)
+        if sys.argv[1:] == ["vlpgrid"]:
+            vlpgrid_golden(tmp)
+            sys.exit(0)
         rng_golden()
         trace_golden(tmp)
         images_and_host(tmp)
         grid_golden(tmp)
         bidir_golden(tmp)
+        vlpgrid_golden(tmp)
     print("golden vectors written to", HERE)
