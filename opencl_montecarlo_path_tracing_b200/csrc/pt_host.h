@@ -114,7 +114,7 @@ struct pt_ctx_s {
     unsigned long long *d_cta_times, *h_cta_times;   // per CTA {start, end} of globaltimer (ns)
     size_t tile_order_cap;
     unsigned char tile_order_key[192];
-    int tile_order_state;         // 0 none, 1 sorted from the 1-spp pre-pass, 2 a full launch is recording, 3 sorted from a full launch
+    int tile_order_state;         // 0 none, 1 the first launch of the geometry is recording (raster order), 2 sorted from its durations
 
     // AUTO kernel choice of the brute-force variants: cached estimate of the pixels that scan the mesh
     double mesh_est;

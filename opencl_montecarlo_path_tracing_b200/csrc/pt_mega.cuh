@@ -10,6 +10,8 @@
 //                 32), and five shuffle-down steps finish the reference's exact reduction tree in
 //                 registers — no scratch image, no second launch, same float sums.
 #pragma once
+#include <time.h>
+
 #include <algorithm>
 #include <utility>
 #include <vector>
@@ -183,11 +185,13 @@ __global__ void __launch_bounds__(256, 4) k_mega_nodof(const __grid_constant__ L
 // the CTA slot-time is used (98.3 % for the full frame on one GPU) — the 11 % the strong-scaling curve lost at N = 8
 // (tools/cta_timeline.py, profiles/r2_09).  The hardware hands out CTAs in block-index order, so the kernel reads its
 // tile from a table sorted by COST, longest first (LPT list scheduling): the cheap tiles fill the end of the launch.
-// Costs are measured, not guessed: the first launch of a geometry runs a 1-spp pre-pass (1/spp of the frame, its output
-// overwritten) in which every CTA records its globaltimer span; the first full launch records again and the table is
-// re-sorted from those exact durations for all later launches of the same geometry.  Which CTA renders which tile never
-// affects results.  (Classifying tiles by "primary ray hits the grid box" was tried first: no gain — floor tiles are as
-// expensive, their shadow rays cross the grid.  1-warp CTAs, to shrink the unit, lost 3 %.)
+// Costs are measured, not guessed: the first launch of a geometry (image size, rows / stripes of this rank, camera, grid)
+// runs in raster order while every CTA records its globaltimer span; every later launch of that geometry uses the table
+// sorted from those durations.  Which CTA renders which tile never affects results, and a table left over from another
+// scene with the same geometry is merely a worse order.  (Tried and dropped: classifying tiles by "primary ray hits the
+// grid box" — no gain, floor tiles are as expensive, their shadow rays cross the grid; a 1-spp pre-pass as the cost
+// estimate for the FIRST launch — its order was no better than raster, one sample per pixel says too little about 256;
+// 1-warp CTAs, to shrink the unit — 3 % slower.)
 struct TileOrderKey {
     int W, H, row_begin, row_end, nrows, stripe_h, rank, nranks, variant_fma, ntri;
     unsigned long long scene_version;
@@ -196,9 +200,17 @@ struct TileOrderKey {
     int res[3];
 };
 
+static double tile_order_now_ms() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec / 1e6;
+}
+
 static int tile_order_rebuild(pt_ctx ctx, size_t n, bool identity) {
+    const double t0 = tile_order_now_ms();
     PT_CUDA(cudaMemcpyAsync(ctx->h_cta_times, ctx->d_cta_times, n * 16, cudaMemcpyDeviceToHost, ctx->stream), "read CTA times");
     PT_CUDA(cudaStreamSynchronize(ctx->stream), "sync CTA times");
+    const double t1 = tile_order_now_ms();
     std::vector<std::pair<unsigned long long, uint32_t>> cost(n);
     for (size_t b = 0; b < n; ++b) {
         const unsigned long long t0 = ctx->h_cta_times[2 * b], t1 = ctx->h_cta_times[2 * b + 1];
@@ -210,6 +222,9 @@ static int tile_order_rebuild(pt_ctx ctx, size_t n, bool identity) {
     });
     for (size_t b = 0; b < n; ++b) ctx->h_tile_order[b] = cost[b].second;
     PT_CUDA(cudaMemcpyAsync(ctx->d_tile_order, ctx->h_tile_order, n * 4, cudaMemcpyHostToDevice, ctx->stream), "upload tile order");
+    if (getenv("PT_DEBUG_AUTO"))
+        fprintf(stderr, "ptcuda: tile order rebuilt for %zu tiles (%s): wait for the GPU %.2f ms, sort %.2f ms\n", n,
+                identity ? "first launch, raster order" : "ordered launch", t1 - t0, tile_order_now_ms() - t1);
     return 0;
 }
 
@@ -232,7 +247,7 @@ static int launch_pixel_b(pt_ctx ctx, const LaunchArgs &args_in) {
             memset(&key, 0, sizeof(key));
             key.W = args.W; key.H = args.H; key.row_begin = args.row_begin; key.row_end = args.row_end; key.nrows = args.nrows;
             key.stripe_h = args.stripe_h; key.rank = args.rank; key.nranks = args.nranks; key.variant_fma = VARIANT * 4 + (FMA ? 2 : 0) + MEM;
-            key.ntri = ctx->ntri_total; key.scene_version = ctx->scene_version; key.cam = args.cam;
+            key.ntri = ctx->ntri_total; key.cam = args.cam;      // (not the scene version: a stale order is only a scheduling hint)
             for (int a = 0; a < 3; ++a) { key.bmin[a] = args.grid.bmin[a]; key.bmax[a] = args.grid.bmax[a]; key.cell[a] = args.grid.cell[a]; key.res[a] = args.grid.res[a]; }
             static_assert(sizeof(TileOrderKey) <= sizeof(ctx->tile_order_key), "tile order key buffer too small");
             if (ctx->tile_order_cap < n) {
@@ -250,24 +265,20 @@ static int launch_pixel_b(pt_ctx ctx, const LaunchArgs &args_in) {
             }
             const bool same = ctx->tile_order_state != 0 && memcmp(&key, ctx->tile_order_key, sizeof(key)) == 0;
             if (!same) {
-                // state 0 -> 1: costs from a 1-spp pre-pass in raster order (image written here is overwritten below)
-                LaunchArgs pre = args;
-                pre.spp = 1; pre.accum = nullptr; pre.rng_out = nullptr; pre.tile_order = nullptr; pre.cta_times = ctx->d_cta_times;
-                k_mega_pixel<VARIANT, FMA, MEM, BIG><<<grid, block, smem, ctx->stream>>>(pre);
-                PT_CUDA(cudaGetLastError(), "launch k_mega_pixel (cost pre-pass)");
-                if (args.counters) PT_CUDA(cudaMemsetAsync(args.counters, 0, 8 * sizeof(unsigned long long), ctx->stream), "clear counters");
-                if (tile_order_rebuild(ctx, n, true)) return 1;
+                // state 1: first launch of this geometry — raster order, every CTA records its span
                 memcpy(ctx->tile_order_key, &key, sizeof(key));
                 ctx->tile_order_state = 1;
-            } else if (ctx->tile_order_state == 2) {
-                // state 2 -> 3: the previous full launch recorded its CTA spans: re-sort from those exact durations, once
-                if (tile_order_rebuild(ctx, n, false)) return 1;
-                ctx->tile_order_state = 3;
+                args.cta_times = ctx->d_cta_times;
+            } else if (ctx->tile_order_state == 1) {
+                // state 1 -> 2: the first launch recorded its CTA spans: sort the tiles by them, once
+                if (tile_order_rebuild(ctx, n, true)) return 1;
+                ctx->tile_order_state = 2;
             }
-            args.tile_order = ctx->d_tile_order;
-            args.tiles_x = grid.x;
-            if (ctx->tile_order_state == 1) { args.cta_times = ctx->d_cta_times; ctx->tile_order_state = 2; }
-            grid = dim3((unsigned)n, 1);
+            if (ctx->tile_order_state == 2) {
+                args.tile_order = ctx->d_tile_order;
+                args.tiles_x = grid.x;
+                grid = dim3((unsigned)n, 1);
+            }
         }
         if (getenv("PT_CTA_TIMES")) {                 // diagnostics: pt_debug_read_scratch() returns the table (block-index order)
             const size_t nb = (size_t)grid.x * grid.y;
