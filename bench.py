@@ -499,7 +499,7 @@ class Ours:
         grid = pt.grid_dims(scene) if w["variant"] == "grid" else None
         if grid is not None:
             r.build_grid(grid)
-        kw = dict(spp=spp, kernel=args.kernel, arith="fma")
+        kw = dict(spp=spp, kernel=args.kernel, arith="fma", dead_rays=args.dead_rays)
         if args.scene_mem:
             kw["scene_mem"] = args.scene_mem
         kw1 = dict(kw)                               # the same launch on one GPU (for the N>1 identity check)
@@ -535,8 +535,22 @@ class Ours:
         for _ in range(warm):
             step()
         torch.cuda.synchronize()
-        counters = r.counters()                      # this rank's share of the frame
+        counters = r.counters()                      # this rank's share of the frame: the work the timed launch really does
         resolved_kernel = r.last_kernel()
+        # The metric counts the REFERENCE's rays (1 ray = 1 TraceRay call of the reference for this frame): with
+        # dead shadow rays elided (the default, include/ptcuda.h pt_render_params.dead_rays) the timed launch traces fewer, so
+        # one untimed launch in TRACE mode supplies the reference's own counts (they equal the oracle's: tests/).
+        counters_ref = counters
+        if args.dead_rays != "trace" and variant != "nodof":
+            kw_t = dict(kw, dead_rays="trace")
+            if world > 1:
+                r.render_device(variant, W, H, SEEDS, rgba.data_ptr(), accum.data_ptr(), **kw_t)
+            else:
+                r.render_device(variant, W, H, SEEDS, rgba.data_ptr(), None, **kw_t)
+            torch.cuda.synchronize()
+            counters_ref = r.counters()
+            step()                                   # leave the buffers as a timed step leaves them
+            torch.cuda.synchronize()
         launches_per_render = {"spec": 2}.get(resolved_kernel, 1)     # PT_KERNEL_SPEC = light pass + heavy pass
         if world > 1:
             dist.barrier()
@@ -561,16 +575,16 @@ class Ours:
         clocks = sampler.finish(t0, t1) if sampler else None
         step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
         total_ms = sum(step_ms)
-        rays, samples = float(counters["rays"]), float(counters["samples"])
+        rays, samples, rays_traced = float(counters_ref["rays"]), float(counters_ref["samples"]), float(counters["rays"])
         per_rank = None
         if world > 1:
             my_kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / max(1, len(kev))
-            tot = torch.tensor([total_ms, rays, samples, my_kernel_ms], dtype=torch.float64, device="cuda")
+            tot = torch.tensor([total_ms, rays, samples, my_kernel_ms, rays_traced], dtype=torch.float64, device="cuda")
             gathered = [torch.zeros_like(tot) for _ in range(world)]
             dist.all_gather(gathered, tot)
             g = torch.stack(gathered).cpu().numpy()
             total_ms = float(g[:, 0].max())          # max over ranks
-            rays, samples = float(g[:, 1].sum()), float(g[:, 2].sum())
+            rays, samples, rays_traced = float(g[:, 1].sum()), float(g[:, 2].sum()), float(g[:, 4].sum())
             km = g[:, 3]
             per_rank = {"render_kernel_ms": {"min": float(km.min()), "mean": float(km.mean()), "max": float(km.max()),
                                              "per_rank": [round(float(x), 4) for x in km]},
@@ -669,10 +683,10 @@ class Ours:
             vpl_info = {"buffer": int(vp.shape[0]), "non_zero": nact, "reference_loop_iterations": counters["vpl_evals"],
                         "executed_evaluations": hit_samples * nact}
         executed = flops_exec / (kernel_ms * 1e-3) / 1e12
-        if variant == "grid":
-            flops_alg = flops_exec                             # per-ray grid work is data dependent: taken from the counters
+        if variant == "grid":                                  # per-ray grid work is data dependent: taken from the TRACE-mode counters
+            flops_alg = F_analytic * counters_ref["rays"] + 58.0 * counters_ref["tri_tests_executed"] + 30.0 * counters_ref["cells_visited"]
         else:
-            flops_alg = F * float(counters["rays"]) + (22.0 * vpl_info["executed_evaluations"] if vpl_info else 0.0)
+            flops_alg = F * float(counters_ref["rays"]) + (22.0 * vpl_info["executed_evaluations"] if vpl_info else 0.0)
         algorithmic = flops_alg / (kernel_ms * 1e-3) / 1e12
         fp32_peak = self.live["fp32_tflops"]
         issue_peak = self.live["mixed_gwarp_inst_per_s"]
@@ -710,6 +724,11 @@ class Ours:
                                       else "8-row stripes round-robin over ranks + one NCCL reduce of the float accumulation buffer")
                                      if world > 1 else "single GPU")),
             "msamples_per_s": samples / 1e3 / ms_per_step, "rays_per_step": rays, "samples_per_step": samples,
+            "rays_traced_per_step": rays_traced,
+            "ray_count": ("rays_per_step = TraceRay calls of the REFERENCE for this frame (device counters of a TRACE-mode launch; equal to "
+                          "the oracle's count) — the unit of `value`, `e2e` and of the reference arm; rays_traced_per_step = rays the timed "
+                          "launch really traced: dead_rays=%s %s" % (args.dead_rays, "(shadow rays of triangle-material samples, whose result "
+                          "the reference never uses, are not traced; same image / accumulation / RNG bits)" if args.dead_rays != "trace" else "")),
             "e2e": {"value": rays / 1e3 / e2e_ms, "unit": "Mrays/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "api": e2e_api},
             "gpu_launches": steps * ((launches_per_render + (2 if bidir else 0)) * world + (1 if world > 1 else 0)),
@@ -775,6 +794,9 @@ def main():
                     help="default: %s at N=1 (BASELINE config 4), %s strong-scaled at N>1 (config 5 at 64 of 4096 spp)" % (DEFAULT_N1, DEFAULT_MULTI))
     ap.add_argument("--kernel", default="auto", choices=["auto", "mega", "persistent", "wavefront"])
     ap.add_argument("--scene-mem", default=None, choices=["auto", "const", "smem"])
+    ap.add_argument("--dead-rays", default="auto", choices=["auto", "elide", "trace"],
+                    help="auto/elide: library default, shadow rays whose result the reference never uses are not traced (same bits); "
+                         "trace: every ray of the reference is traced")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="N=1 default run: skip the other BASELINE configs")
     ap.add_argument("--no-parity", action="store_true")

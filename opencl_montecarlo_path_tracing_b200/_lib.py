@@ -69,6 +69,7 @@ class pt_render_params(C.Structure):
         ("sample_blocks", C.c_int32),
         ("n_vlp", C.c_int32),
         ("cluster_cull", C.c_int32),
+        ("dead_rays", C.c_int32),
     ]
 
 

@@ -172,7 +172,9 @@ class RenderResult:
 
 def make_params(variant, width, height, seeds, spp=64, kernel="auto", scene_mem=None, arith="fma", rows=None,
                 want_accum=False, want_rng=False, interleave=0, rank=0, nranks=1, cull=True, n_vlp=0, sample_block=0, sample_blocks=0,
-                cluster_cull="auto"):
+                cluster_cull="auto", dead_rays="auto"):
+    """dead_rays: "auto" / "elide" — shadow rays of triangle-material samples (their result is never used) are not traced;
+    "trace" — every ray of the reference is traced and the work counters equal the reference's (include/ptcuda.h)."""
     p = pt_render_params()
     p.variant = PT_VARIANT[variant]
     p.width, p.height, p.spp = int(width), int(height), int(spp)
@@ -190,6 +192,7 @@ def make_params(variant, width, height, seeds, spp=64, kernel="auto", scene_mem=
     p.n_vlp = int(n_vlp)
     p.sample_block, p.sample_blocks = int(sample_block), int(sample_blocks)
     p.cluster_cull = {"auto": 0, "on": 1, "off": 2}[cluster_cull]
+    p.dead_rays = {"auto": 0, "trace": 1, "elide": 2}[dead_rays]
     return p
 
 

@@ -361,7 +361,7 @@ int pt_vlp_grid_build_device(pt_ctx ctx, const pt_grid *g) {
     const int n = ctx->nvpl;
     GridDev G;
     for (int a = 0; a < 3; ++a) { G.bmin[a] = g->box_min[a]; G.bmax[a] = g->box_max[a]; G.cell[a] = g->cell_size[a]; G.res[a] = g->res[a]; }
-    G.cells = nullptr; G.recs = nullptr; G.sph = nullptr; G.sph_k = INFINITY;
+    G.cells = nullptr; G.cells_pad = nullptr; G.pad_sx = G.res[0] + 2; G.pad_sxy = G.pad_sx * (G.res[1] + 2); G.recs = nullptr; G.sph = nullptr; G.sph_k = INFINITY;
     const int nblocks = (int)((ncells + SCAN_BLOCK - 1) / SCAN_BLOCK);
     if (grow_buf((void **)&ctx->gb_count, &ctx->gb_cap[0], ncells * 4, "alloc grid count")) return 1;
     if (grow_buf((void **)&ctx->gb_raw_start, &ctx->gb_cap[1], (ncells + 1) * 4, "alloc grid start")) return 1;
@@ -397,6 +397,16 @@ int pt_vlp_grid_build_device(pt_ctx ctx, const pt_grid *g) {
     return 0;
 }
 
+// cells -> cells inside a one-cell border of sentinel words (GridDev::cells_pad); one thread per padded cell
+__global__ void k_grid_pad(const uint2 *__restrict__ cells, int rx, int ry, int rz, uint2 *__restrict__ pad) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t sx = rx + 2, sy = ry + 2, n = sx * sy * (size_t)(rz + 2);
+    if (i >= n) return;
+    const int x = (int)(i % sx) - 1, y = (int)((i / sx) % sy) - 1, z = (int)(i / (sx * sy)) - 1;
+    const bool in = x >= 0 && x < rx && y >= 0 && y < ry && z >= 0 && z < rz;
+    pad[i] = in ? cells[((size_t)z * ry + y) * rx + x] : make_uint2(0u, 0xFFFFFFFFu);
+}
+
 int pt_grid_build_device(pt_ctx ctx, const pt_grid *g) {
     using namespace pt;
     const size_t ncells = (size_t)g->res[0] * g->res[1] * g->res[2];
@@ -406,7 +416,10 @@ int pt_grid_build_device(pt_ctx ctx, const pt_grid *g) {
     for (int a = 0; a < 3; ++a) {
         G.bmin[a] = g->box_min[a]; G.bmax[a] = g->box_max[a]; G.cell[a] = g->cell_size[a]; G.res[a] = g->res[a];
     }
-    G.cells = nullptr; G.recs = nullptr; G.sph = nullptr; G.sph_k = INFINITY;
+    G.cells = nullptr; G.cells_pad = nullptr; G.pad_sx = G.res[0] + 2; G.pad_sxy = G.pad_sx * (G.res[1] + 2); G.recs = nullptr; G.sph = nullptr; G.sph_k = INFINITY;
+    const size_t npad = (size_t)(g->res[0] + 2) * (g->res[1] + 2) * (g->res[2] + 2);
+    if (g->res[0] < 1 || g->res[1] < 1 || g->res[2] < 1 || npad >= (1ull << 31))
+        return pt_fail(1, "pt_build_grid: grid resolution %d x %d x %d out of range", g->res[0], g->res[1], g->res[2]);
 
     // All buffers of the build live in the context and only ever grow: cudaMalloc / cudaFree of the ~250 MB a 1 M-
     // triangle grid needs cost 80 ms per build, 300x the 0.24 ms the nine kernels take.
@@ -426,6 +439,7 @@ int pt_grid_build_device(pt_ctx ctx, const pt_grid *g) {
     if (grow((void **)&ctx->gb_bsums, &ctx->gb_cap[3], (size_t)(nblocks + 1) * 4, "alloc scan sums")) return 1;
     if (grow((void **)&ctx->d_cell_start, &ctx->gb_cap[4], (ncells + 1) * 4, "alloc cell_start")) return 1;
     if (grow((void **)&ctx->d_cells, &ctx->gb_cap[5], ncells * sizeof(uint2), "alloc cells")) return 1;
+    if (grow((void **)&ctx->d_cells_pad, &ctx->gb_cap[11], npad * sizeof(uint2), "alloc padded cells")) return 1;
     uint32_t *d_count = ctx->gb_count, *d_raw_start = ctx->gb_raw_start, *d_cursor = ctx->gb_cursor, *d_bsums = ctx->gb_bsums;
     PT_CUDA(cudaMemsetAsync(d_count, 0, ncells * 4, ctx->stream), "memset");
     PT_CUDA(cudaMemsetAsync(d_cursor, 0, ncells * 4, ctx->stream), "memset");
@@ -457,9 +471,12 @@ int pt_grid_build_device(pt_ctx ctx, const pt_grid *g) {
                                                                         ctx->d_cell_start, ctx->d_refs, ctx->d_recs, ctx->d_sph,
                                                                         ctx->d_cells);
     PT_CUDA(cudaGetLastError(), "grid emit");
+    k_grid_pad<<<(unsigned)((npad + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_cells, g->res[0], g->res[1], g->res[2], ctx->d_cells_pad);
+    PT_CUDA(cudaGetLastError(), "grid pad");
     // no synchronisation here: the render that follows is ordered behind the build on the same stream
 
     G.cells = ctx->d_cells;
+    G.cells_pad = ctx->d_cells_pad;
     G.recs = ctx->d_recs;
     G.sph = ctx->d_sph;
     {

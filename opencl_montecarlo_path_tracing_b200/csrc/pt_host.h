@@ -71,6 +71,7 @@ struct pt_ctx_s {
     pt_grid grid_desc;
     pt::GridDev grid;
     uint2 *d_cells;
+    uint2 *d_cells_pad;           // the same words inside a one-cell sentinel border (GridDev::cells_pad)
     float4 *d_recs;
     float4 *d_sph;                // per record: bounding sphere of its triangle (sphere prefilter of the traversal)
     uint32_t *gb_kmax;            // bit pattern of max |e0||e2| over the mesh (grid build)
@@ -79,7 +80,7 @@ struct pt_ctx_s {
     uint64_t total_refs;
     size_t ncells;
     uint32_t *gb_count, *gb_raw_start, *gb_cursor, *gb_bsums, *gb_raw_refs;   // build scratch, kept between builds
-    size_t gb_cap[11];            // capacities (bytes) of the five scratch buffers, cell_start, cells, refs, recs
+    size_t gb_cap[12];            // capacities (bytes) of the five scratch buffers, cell_start, cells, refs, recs
 
     // VLP grid of CLSuperMetropolisPathTracer_vlpgrid on the context's VLP buffer (pt_build_vlp_grid)
     bool vlp_grid_set;

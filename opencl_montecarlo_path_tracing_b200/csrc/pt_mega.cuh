@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(128, (BIG && VARIANT == PT_VARIANT_GRID) ? 8 :
         if (P.accum) P.accum[pix] = make_float4(cx, cy, cz, P.alpha);
         if (P.rng_out) P.rng_out[pix] = make_uint4(rng.x0, rng.x1, rng.c0, rng.c1);
     }
+    if (GRID) cnt.btests = cnt.gtri;        // trace_grid tests every record of the cells it visits
     flush_counters(P, cnt, GRID ? 0 : S->ntri_counted, P.ap.nsq + P.ap.nsp);
     if (BIG && P.cta_times && threadIdx.x == 0) {
         unsigned long long t_end;

@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(128, 6) k_sm_pixel(const __grid_constant__ Lau
             }
         }
     }
+    if (GRID) cnt.btests = cnt.gtri;        // trace_grid tests every record of the cells it visits
     flush_counters(P, cnt, GRID ? 0 : S->ntri_counted, P.ap.nsq + P.ap.nsp);
 }
 

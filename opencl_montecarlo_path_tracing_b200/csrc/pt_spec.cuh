@@ -121,7 +121,7 @@ PT_DEV V3 sample_rounds(const AnalyticParams &AP, const SceneBlock *S, const Gri
                 float r0, r1;
                 rng_next(rng, r0, r1);                                  // drawn before any skip (base:168)
                 const float4 L = AP.lights[l];
-                if (!(!CARRY && L.w == 0.0f)) {                         // base:171 only
+                if (!(!CARRY && L.w == 0.0f) && !(AP.elide_dead && m == 4)) {   // base:171 only; dead shadow rays: AnalyticParams::elide_dead
                     light_dir<FMA>(L, r0, r1, X, n, rd, lam);
                     if (!(lam < 0.0f)) { ro = X; cnt.shadow++; has_ray = true; }
                 }

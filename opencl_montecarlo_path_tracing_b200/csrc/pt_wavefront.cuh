@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(256) wf_intersect(const __grid_constant__ Laun
         B.rayO[idx].w = t;
         B.rayD[idx].w = __int_as_float(hit);
     }
+    if (GRID) cnt.btests = cnt.gtri;        // trace_grid tests every record of the cells it visits
     flush_counters(P, cnt, GRID ? 0 : S->ntri_counted, P.ap.nsq + P.ap.nsp);
 }
 

@@ -170,7 +170,7 @@ extern "C" void pt_destroy(pt_ctx c) {
         cudaFree(c->d_scene[a]);
     }
     cudaFree(c->d_tris_raw);
-    cudaFree(c->d_cells); cudaFree(c->d_recs); cudaFree(c->d_refs); cudaFree(c->d_cell_start); cudaFree(c->d_sph); cudaFree(c->gb_kmax);
+    cudaFree(c->d_cells); cudaFree(c->d_cells_pad); cudaFree(c->d_recs); cudaFree(c->d_refs); cudaFree(c->d_cell_start); cudaFree(c->d_sph); cudaFree(c->gb_kmax);
     cudaFree(c->gb_count); cudaFree(c->gb_raw_start); cudaFree(c->gb_cursor); cudaFree(c->gb_bsums); cudaFree(c->gb_raw_refs);
     cudaFree(c->d_rgba); cudaFree(c->d_accum); cudaFree(c->d_rng); cudaFree(c->d_counters); cudaFree(c->d_scratch);
     cudaFree(c->d_tile_order); cudaFree(c->d_cta_times);
@@ -661,6 +661,13 @@ static int fill_args(pt_ctx c, const pt_camera *cam, const pt_render_params *p, 
             A->ap.box_lo[a] = p->no_cull ? -INFINITY : lo[a];      // the per-ray margin is added on the device
             A->ap.box_hi[a] = p->no_cull ? INFINITY : hi[a];
         }
+    }
+    {
+        static int env = -2;                      // PT_DEAD_RAYS=trace|elide overrides AUTO
+        if (env == -2) { const char *e = getenv("PT_DEAD_RAYS"); env = !e ? -1 : (e[0] == 't' || e[0] == 'T' || e[0] == '1') ? 1 : 0; }
+        bool trace = p->dead_rays == PT_DEAD_RAYS_TRACE || p->no_cull;
+        if (p->dead_rays == PT_DEAD_RAYS_AUTO && env >= 0) trace = env == 1 || p->no_cull;
+        A->ap.elide_dead = trace ? 0 : 1;
     }
     A->ap.ntri_hint = p->variant == PT_VARIANT_GRID ? 0 : hs->ntri;
     A->ap.tri_coop = 0;    // set by the launchers that stage the records in shared memory

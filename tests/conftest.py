@@ -12,6 +12,12 @@ REF_BUILD = os.path.join(ROOT, "oracle", "_ref")
 
 SEED_SETS = [(1, 2, 3, 4), (123456789, 42, 7, 99999)]
 
+# The parity tests compare the WORK COUNTERS with the oracle's as well, so by default they run the kernels in
+# PT_DEAD_RAYS_TRACE mode (every ray of the reference is traced; include/ptcuda.h).  The library default — shadow rays of
+# triangle-material samples elided, same image / accumulation / RNG bits — is what tests/test_dead_rays_gpu.py pins, with
+# an explicit dead_rays="elide" and through the drop-in executables with this variable removed.
+os.environ["PT_DEAD_RAYS"] = "trace"
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")

@@ -27,7 +27,7 @@ with pt.Renderer(0) as r:
     for kernel in os.environ.get("QG_KERNELS", "mega,persistent,grid_tma").split(","):
         best = 1e9
         for it in range(3):
-            res = r.render("grid", W, H, (1, 2, 3, 4), spp=spp, kernel=kernel, read_image=False)
+            res = r.render("grid", W, H, (1, 2, 3, 4), spp=spp, kernel=kernel, read_image=False, dead_rays=os.environ.get("QG_DEAD", "auto"))
             best = min(best, res.ms)
         c = res.counters
         print("grid soup n=%d %-10s %dx%d spp %d: %9.3f ms  %8.1f Mrays/s %8.1f Msamples/s  cells/ray %.2f tests/ray %.2f exact/ray %.2f" % (
