@@ -251,7 +251,7 @@ static int launch_stream_grid(pt_ctx ctx, const LaunchArgs &args_in) {
     if (per_sm < 1) per_sm = 1;
     uint32_t blocks = (uint32_t)(ctx->sm_count * per_sm);
     const uint32_t need_blocks = (nitems + 127) / 128;
-    if (blocks > need_blocks) blocks = need_blocks;
+    if (blocks > need_blocks || getenv("PT_STREAM_ALL")) blocks = need_blocks;   // PT_STREAM_ALL: one item per lane, no regeneration (each lane keeps its pixel)
     if (pt_ensure_scratch(ctx, 256)) return 1;
     uint32_t *counter = (uint32_t *)ctx->d_scratch;
     const uint32_t first_free = blocks * 128u;       // items [0, first_free) are the initial assignment

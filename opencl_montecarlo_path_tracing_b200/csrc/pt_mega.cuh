@@ -229,8 +229,10 @@ static int tile_order_rebuild(pt_ctx ctx, size_t n, bool identity) {
     return 0;
 }
 
+// `other`: another kernel with k_mega_pixel's tiling and launch contract (PT_KERNEL_GRID_QUEUE) to launch in its place
 template <int VARIANT, bool FMA, int MEM, bool BIG>
-static int launch_pixel_b(pt_ctx ctx, const LaunchArgs &args_in) {
+static int launch_pixel_b(pt_ctx ctx, const LaunchArgs &args_in, void (*other)(const LaunchArgs) = nullptr) {
+    void (*kern)(const LaunchArgs) = other ? other : k_mega_pixel<VARIANT, FMA, MEM, BIG>;
     LaunchArgs args = args_in;
     args.ap.tri_coop = MEM == PT_SCENE_SMEM;
     dim3 grid((args.W + 15) / 16, (args.nrows + 7) / 8), block(128);
@@ -247,7 +249,7 @@ static int launch_pixel_b(pt_ctx ctx, const LaunchArgs &args_in) {
             TileOrderKey key;
             memset(&key, 0, sizeof(key));
             key.W = args.W; key.H = args.H; key.row_begin = args.row_begin; key.row_end = args.row_end; key.nrows = args.nrows;
-            key.stripe_h = args.stripe_h; key.rank = args.rank; key.nranks = args.nranks; key.variant_fma = VARIANT * 4 + (FMA ? 2 : 0) + MEM;
+            key.stripe_h = args.stripe_h; key.rank = args.rank; key.nranks = args.nranks; key.variant_fma = VARIANT * 4 + (FMA ? 2 : 0) + MEM + (other ? 64 : 0);
             key.ntri = ctx->ntri_total; key.cam = args.cam;      // (not the scene version: a stale order is only a scheduling hint)
             for (int a = 0; a < 3; ++a) { key.bmin[a] = args.grid.bmin[a]; key.bmax[a] = args.grid.bmax[a]; key.cell[a] = args.grid.cell[a]; key.res[a] = args.grid.res[a]; }
             static_assert(sizeof(TileOrderKey) <= sizeof(ctx->tile_order_key), "tile order key buffer too small");
@@ -286,13 +288,13 @@ static int launch_pixel_b(pt_ctx ctx, const LaunchArgs &args_in) {
             if (pt_ensure_scratch(ctx, nb * 16 + 256)) return 1;
             unsigned long long *diag = (unsigned long long *)((char *)ctx->d_scratch + 256);
             if (!args.cta_times) { args.cta_times = diag; diag = nullptr; }
-            k_mega_pixel<VARIANT, FMA, MEM, BIG><<<grid, block, smem, ctx->stream>>>(args);
+            kern<<<grid, block, smem, ctx->stream>>>(args);
             PT_CUDA(cudaGetLastError(), "launch k_mega_pixel");
             if (diag) PT_CUDA(cudaMemcpyAsync(diag, args.cta_times, nb * 16, cudaMemcpyDeviceToDevice, ctx->stream), "copy CTA times");
             return 0;
         }
     }
-    k_mega_pixel<VARIANT, FMA, MEM, BIG><<<grid, block, smem, ctx->stream>>>(args);
+    kern<<<grid, block, smem, ctx->stream>>>(args);
     PT_CUDA(cudaGetLastError(), "launch k_mega_pixel");
     return 0;
 }

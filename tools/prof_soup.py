@@ -14,5 +14,5 @@ with pt.Renderer(0) as r:
     r.set_scene(scene); r.build_grid(pt.grid_dims(scene))
     for k in os.environ.get("PS_KERNEL", "auto").split(","):
         for it in range(int(os.environ.get("PS_REPS", "2"))):
-            res = r.render("grid", W, H, (1, 2, 3, 4), spp=int(os.environ.get("PS_SPP", "4")), kernel=k, read_image=False)
+            res = r.render("grid", W, H, (1, 2, 3, 4), spp=int(os.environ.get("PS_SPP", "4")), kernel=k, read_image=False, dead_rays=os.environ.get("PS_DEAD", "auto"))
         print(k, res.ms, res.counters, flush=True)
