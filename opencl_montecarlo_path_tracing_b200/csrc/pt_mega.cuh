@@ -104,8 +104,10 @@ __global__ void __launch_bounds__(128, (BIG && VARIANT == PT_VARIANT_GRID) ? 8 :
         const uint32_t tile = __ldg(P.tile_order + blockIdx.x);
         by = tile / P.tiles_x; bx = tile - by * P.tiles_x;
     }
-    const int i = bx * 16 + (warp & 1) * 8 + (lane & 7);
-    const int vr = by * 8 + (warp >> 1) * 4 + (lane >> 3);
+    // 4 warps: 16x8 pixel tile (2x2 warps of 8x4 pixels); 2 warps: 16x4; 1 warp: 8x4 (launch_pixel_b picks the block size)
+    const int tw = blockDim.x >= 64 ? 2 : 1, th = (int)(blockDim.x >> 5) / tw;
+    const int i = bx * (8 * tw) + (warp % tw) * 8 + (lane & 7);
+    const int vr = by * (4 * th) + (warp / tw) * 4 + (lane >> 3);
     Counters cnt = {0, 0, 0, 0, 0, 0};
     const int j = map_row(P, vr);
     if (i < P.W && vr < P.nrows && j < P.row_end) {
@@ -236,6 +238,14 @@ static int launch_pixel_b(pt_ctx ctx, const LaunchArgs &args_in, void (*other)(c
     LaunchArgs args = args_in;
     args.ap.tri_coop = MEM == PT_SCENE_SMEM;
     dim3 grid((args.W + 15) / 16, (args.nrows + 7) / 8), block(128);
+    if (BIG && VARIANT == PT_VARIANT_GRID && !other) {
+        // Warps of one CTA finish at different times and hold their registers until the last one does (ncu: 1.5 of ~8 warps
+        // per scheduler wait at the final barrier).  Smaller CTAs return those slots earlier; PT_MEGA_WARPS = 1 | 2 | 4.
+        static int nw = -1;
+        if (nw == -1) { const char *e = getenv("PT_MEGA_WARPS"); nw = e ? atoi(e) : 4; if (nw != 1 && nw != 2) nw = 4; }
+        if (nw == 2) { grid = dim3((args.W + 15) / 16, (args.nrows + 3) / 4); block = dim3(64); }
+        if (nw == 1) { grid = dim3((args.W + 7) / 8, (args.nrows + 3) / 4); block = dim3(32); }
+    }
     const size_t smem = MEM == PT_SCENE_SMEM ? (size_t)args.scene_bytes : 0;
     if (smem > 48 * 1024)
         PT_CUDA(cudaFuncSetAttribute(k_mega_pixel<VARIANT, FMA, MEM, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
@@ -249,7 +259,7 @@ static int launch_pixel_b(pt_ctx ctx, const LaunchArgs &args_in, void (*other)(c
             TileOrderKey key;
             memset(&key, 0, sizeof(key));
             key.W = args.W; key.H = args.H; key.row_begin = args.row_begin; key.row_end = args.row_end; key.nrows = args.nrows;
-            key.stripe_h = args.stripe_h; key.rank = args.rank; key.nranks = args.nranks; key.variant_fma = VARIANT * 4 + (FMA ? 2 : 0) + MEM + (other ? 64 : 0);
+            key.stripe_h = args.stripe_h; key.rank = args.rank; key.nranks = args.nranks; key.variant_fma = VARIANT * 4 + (FMA ? 2 : 0) + MEM + (other ? 64 : 0) + (int)block.x * 128;
             key.ntri = ctx->ntri_total; key.cam = args.cam;      // (not the scene version: a stale order is only a scheduling hint)
             for (int a = 0; a < 3; ++a) { key.bmin[a] = args.grid.bmin[a]; key.bmax[a] = args.grid.bmax[a]; key.cell[a] = args.grid.cell[a]; key.res[a] = args.grid.res[a]; }
             static_assert(sizeof(TileOrderKey) <= sizeof(ctx->tile_order_key), "tile order key buffer too small");

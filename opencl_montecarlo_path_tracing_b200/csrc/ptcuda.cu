@@ -28,6 +28,7 @@
 #include "pt_gridpool.cuh"
 #include "pt_spec.cuh"
 #include "pt_gridqueue.cuh"
+#include "pt_gridasync.cuh"
 
 // ------------------------------------------------------------------------------------ errors
 static std::atomic<int> g_error_mode{PT_ERRORS_EXIT};
@@ -774,6 +775,9 @@ static int dispatch(pt_ctx c, const pt_render_params *pin, const pt::LaunchArgs 
         case PT_KERNEL_GRID_QUEUE:
             if (p->variant != PT_VARIANT_GRID) return pt_fail(1, "PT_KERNEL_GRID_QUEUE applies to the trianglegrid variant only");
             return pt_launch_grid_queue(c, p, A);
+        case PT_KERNEL_GRID_ASYNC:
+            if (p->variant != PT_VARIANT_GRID) return pt_fail(1, "PT_KERNEL_GRID_ASYNC applies to the trianglegrid variant only");
+            return pt_launch_grid_async(c, p, A);
         case PT_KERNEL_WAVEFRONT: return pt_launch_wavefront(c, p, A);
         case PT_KERNEL_GRID_TMA: return pt_launch_grid_tma(c, p, A);
     }

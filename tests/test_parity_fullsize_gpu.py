@@ -82,7 +82,7 @@ def test_soup1m_device_grid_equals_oracle_grid(soup_renderer, soup1m, oracle_fma
 
 
 @pytest.mark.parametrize("arith", ["fma", "separate"])
-@pytest.mark.parametrize("kernel", ["auto", "mega", "persistent", "grid_pool", "grid_queue"])
+@pytest.mark.parametrize("kernel", ["auto", "mega", "persistent", "grid_pool", "grid_queue", "grid_async"])
 def test_config4_soup1m_1920x1080x256_windows(soup_renderer, soup1m, oracle_fma, oracle_sep, arith, kernel):
     r, g = soup_renderer
     o = oracle_fma if arith == "fma" else oracle_sep

@@ -151,7 +151,8 @@ def _soup_scene(n, seed, box):
 @pytest.mark.parametrize("n,box,kernel", [(30000, 24.0, "mega"), (30000, 24.0, "persistent"), (30000, 24.0, "wavefront"),
                                           (30000, 24.0, "grid_tma"), (30000, 24.0, "grid_stream"), (70000, 30.0, "mega"),
                                           (70000, 30.0, "grid_stream"), (30000, 24.0, "grid_pool"), (70000, 30.0, "grid_pool"),
-                                          (30000, 24.0, "grid_queue"), (70000, 30.0, "grid_queue")])
+                                          (30000, 24.0, "grid_queue"), (70000, 30.0, "grid_queue"),
+                                          (30000, 24.0, "grid_async"), (70000, 30.0, "grid_async")])
 def test_grid_synthetic_soup_bit_exact(renderer, oracle_fma, n, box, kernel):
     """Uniform-grid traversal on a seeded triangle soup (the config-4/5 generator at test size); 70000
     triangles exceed the reference's 16-bit cell ids (wide ids).  The camera sits inside the box."""
@@ -174,7 +175,7 @@ def test_grid_synthetic_soup_bit_exact(renderer, oracle_fma, n, box, kernel):
     assert res.counters["cells_visited"] > 0 and res.counters["tri_tests"] > 0
 
 
-@pytest.mark.parametrize("kernel", ["grid_tma", "grid_stream", "grid_pool", "grid_queue"])
+@pytest.mark.parametrize("kernel", ["grid_tma", "grid_stream", "grid_pool", "grid_queue", "grid_async"])
 def test_grid_tma_default_scene_and_dense_cells(renderer, scene_dirs, oracle_fma, kernel):
     """TMA-staged warp-per-ray traversal and cell-granular regeneration: default grid scene, and CELL_SIZE_MODIFIER 0.02
     (one fat cell capped at 62)."""
