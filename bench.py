@@ -764,7 +764,7 @@ def bench_ours(args, wname, default_workload):
             for name in EXTRA_N1:
                 heavy = WORKLOADS[name]["W"] * WORKLOADS[name]["H"] * WORKLOADS[name]["spp"] > 1 << 26
                 sub = b.measure(name, min(args.steps, 5 if heavy else 50), 3, headline=False)
-                keep = ("value", "unit", "ms_per_step", "steps", "msamples_per_s", "rays_per_step", "samples_per_step", "e2e", "parity_check",
+                keep = ("value", "unit", "ms_per_step", "steps", "msamples_per_s", "rays_per_step", "rays_traced_per_step", "samples_per_step", "e2e", "parity_check",
                         "roofline", "cpu_baseline", "reference_opencl_same_gpu", "gpu_launches")
                 extras[name] = dict({"baseline_config": WORKLOADS[name]["config"], "description": WORKLOADS[name]["desc"]},
                                     **{k: sub[k] for k in keep if k in sub})

@@ -12,7 +12,9 @@
  * Extensions are env-only so the command line stays a drop-in:
  *   PT_SEEDS=a,b,c,d   fixed seeds (default: wall-clock recipe of the reference)
  *   PT_SPP=n           samples per pixel (default 64)
- *   PT_KERNEL=auto|mega|persistent|wavefront|grid_tma|grid_stream|grid_pool|spec     PT_SCENE_MEM=auto|const|smem     PT_ARITH=fma|separate
+ *   PT_KERNEL=auto|mega|persistent|wavefront|grid_tma|grid_stream|grid_pool|spec|grid_queue|grid_async
+ *   PT_SCENE_MEM=auto|const|smem     PT_ARITH=fma|separate
+ *   PT_DEAD_RAYS=trace|elide   (read by libptcuda) trace the shadow rays whose result the reference never uses / skip them (default)
  *   PT_NO_CULL=1       run the full brute-force triangle loop for every ray (default: rays whose line misses
  *                      the mesh's bounding sphere skip it; identical results)
  *   PT_MAX_TRIANGLES=n lift the 512 / 65536 MAX_TRIANGLES cap of the reference hosts
@@ -253,7 +255,7 @@ int pth_cli_main(int variant, int argc, char **argv) {
     if (grid) grid_evt = multi ? pt_multi_build_grid(multi, &gdesc) : pt_build_grid(ctx, &gdesc);
     tick("build grid (enqueue)");
 
-    static const char *const kernels[] = {"mega", "persistent", "wavefront", "auto", "grid_tma", "grid_stream", "grid_pool", "spec"};
+    static const char *const kernels[] = {"mega", "persistent", "wavefront", "auto", "grid_tma", "grid_stream", "grid_pool", "spec", "grid_queue", "grid_async"};
     static const char *const mems[] = {"const", "smem", "auto"};
     static const char *const ariths[] = {"separate", "fma"};
     pt_render_params rp;
@@ -263,7 +265,7 @@ int pth_cli_main(int variant, int argc, char **argv) {
     rp.height = img_height;
     rp.spp = getenv("PT_SPP") ? atoi(getenv("PT_SPP")) : 64;
     memcpy(rp.seeds, seeds, sizeof(seeds));
-    rp.kernel = env_choice("PT_KERNEL", kernels, 8, PT_KERNEL_AUTO);
+    rp.kernel = env_choice("PT_KERNEL", kernels, 10, PT_KERNEL_AUTO);
     rp.scene_mem = env_choice("PT_SCENE_MEM", mems, 3, PT_SCENE_AUTO);
     rp.arith = env_choice("PT_ARITH", ariths, 2, PT_ARITH_FMA);
     rp.no_cull = getenv("PT_NO_CULL") ? atoi(getenv("PT_NO_CULL")) : 0;

@@ -32,8 +32,10 @@ struct SpecEntry {            // 48 bytes
     uint4 rng;                // state at the start of sample `sdone`
 };
 
+// 72 registers / 7 CTAs per SM: at 64 the pass spills inside the sample loop (base 512x512 light pass 0.57 ms, issue slots 58 %,
+// long-scoreboard stalls on local memory), at 80 it loses more occupancy than it gains: whole frame 1.05 / 0.87 / 0.92 ms.
 template <int VARIANT, bool FMA>
-__global__ void __launch_bounds__(128, 8) k_spec_light(const __grid_constant__ LaunchArgs P, SpecEntry *queue, uint32_t *queue_len, int scan_budget) {
+__global__ void __launch_bounds__(128, 7) k_spec_light(const __grid_constant__ LaunchArgs P, SpecEntry *queue, uint32_t *queue_len, int scan_budget) {
     constexpr bool CARRY = VARIANT != PT_VARIANT_BASE;
     const SceneBlock *S = &c_scene;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -144,7 +146,7 @@ PT_DEV V3 sample_rounds(const AnalyticParams &AP, const SceneBlock *S, const Gri
             }
         }
         __syncwarp(lanes);
-        if (AP.ntri_hint != 0) tri_loop<FMA, CL>(AP, S, AP.tri_coop != 0, need, ro, rd, t, hit, cnt, lanes);
+        if (AP.ntri_hint != 0) tri_loop<FMA, CL, false>(AP, S, AP.tri_coop != 0, need, ro, rd, t, hit, cnt, lanes);
         __syncwarp(lanes);
         if (l < 0) {
             primary_hit = active && hit != HIT_NONE;
