@@ -397,6 +397,7 @@ int pt_vlp_grid_build_device(pt_ctx ctx, const pt_grid *g) {
     return 0;
 }
 
+namespace pt {
 // cells -> cells inside a one-cell border of sentinel words (GridDev::cells_pad); one thread per padded cell
 __global__ void k_grid_pad(const uint2 *__restrict__ cells, int rx, int ry, int rz, uint2 *__restrict__ pad) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -406,6 +407,7 @@ __global__ void k_grid_pad(const uint2 *__restrict__ cells, int rx, int ry, int 
     const bool in = x >= 0 && x < rx && y >= 0 && y < ry && z >= 0 && z < rz;
     pad[i] = in ? cells[((size_t)z * ry + y) * rx + x] : make_uint2(0u, 0xFFFFFFFFu);
 }
+}  // namespace pt
 
 int pt_grid_build_device(pt_ctx ctx, const pt_grid *g) {
     using namespace pt;
