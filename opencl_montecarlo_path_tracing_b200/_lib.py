@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_DIR = os.path.join(_HERE, "lib")
 BIN_DIR = os.path.join(_HERE, "bin")
 
-PT_VARIANT = {"base": 0, "lmem": 1, "nodof": 2, "grid": 3, "bidir": 4}
+PT_VARIANT = {"base": 0, "lmem": 1, "nodof": 2, "grid": 3, "bidir": 4, "vlpgrid": 5}
 PT_KERNEL = {"mega": 0, "persistent": 1, "wavefront": 2, "auto": 3, "grid_tma": 4, "grid_stream": 5, "grid_pool": 6, "spec": 7, "grid_queue": 8, "grid_async": 9}
 PT_SCENE_MEM = {"const": 0, "smem": 1, "auto": 2}
 PT_ARITH = {"separate": 0, "fma": 1}

@@ -32,6 +32,11 @@ struct LaunchArgs {
     unsigned long long *cta_times; // diagnostics (PT_CTA_TIMES=1, big-grid megakernel): per CTA {start ns, end ns} of globaltimer
     const float4 *vpl;             // bidirectional variant: non-zero VPLs, dense, in buffer order
     const int *nvpl_active;        //   their number (device memory: written by k_compact_vpls)
+    // PT_VARIANT_VLPGRID: the raw VPL buffer and the VLP grid (CSR, lists in ascending light order, <= 62 per cell); NULL otherwise
+    const float4 *vpl_raw;
+    const uint32_t *vg_start, *vg_refs;
+    float vg_bmin[3], vg_cell[3];
+    int vg_res[3];
 };
 
 // virtual row -> image row (identity, or the rank's interleaved stripes)

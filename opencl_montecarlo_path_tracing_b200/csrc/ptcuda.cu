@@ -555,9 +555,12 @@ static int ensure_dev(void **p, size_t *cap, size_t bytes) {
 
 static int validate_params(pt_ctx c, const pt_render_params *p) {
     if (!c->scene_set) return pt_fail(1, "render: call pt_set_scene first");
-    if (p->variant < 0 || p->variant > PT_VARIANT_BIDIR) return pt_fail(1, "render: unknown variant %d", p->variant);
-    if (p->variant == PT_VARIANT_BIDIR && !c->vpls_set)
-        return pt_fail(1, "render: the bidirectional variant needs pt_launch_lighttracer (or pt_set_vpls) first");
+    if (p->variant < 0 || p->variant > PT_VARIANT_VLPGRID) return pt_fail(1, "render: unknown variant %d", p->variant);
+    if ((p->variant == PT_VARIANT_BIDIR || p->variant == PT_VARIANT_VLPGRID) && !c->vpls_set)
+        return pt_fail(1, "render: the bidirectional variants need pt_launch_lighttracer (or pt_set_vpls) first");
+    if (p->variant == PT_VARIANT_VLPGRID && !c->vlp_grid_set)
+        return pt_fail(1, "render: the vlpgrid variant needs pt_build_vlp_grid first");
+    if (p->variant == PT_VARIANT_VLPGRID && p->sample_blocks > 1) return pt_fail(1, "render: sample sharding is not defined for the vlpgrid variant");
     if (p->width <= 0 || p->height <= 0) return pt_fail(1, "render: bad image size %dx%d", p->width, p->height);
     if (p->spp <= 0) return pt_fail(1, "render: spp must be positive");
     if (p->variant == PT_VARIANT_NODOF && p->spp != 64) return pt_fail(1, "render: the NoDoF variant is defined for 64 samples (8x8 work-items) per pixel");
@@ -674,6 +677,10 @@ static int fill_args(pt_ctx c, const pt_camera *cam, const pt_render_params *p, 
     A->ap.ntri_hint = p->variant == PT_VARIANT_GRID ? 0 : hs->ntri;
     A->ap.tri_coop = 0;    // set by the launchers that stage the records in shared memory
     A->vpl = c->d_vpl_active; A->nvpl_active = c->d_vpl_count;
+    if (p->variant == PT_VARIANT_VLPGRID) {
+        A->vpl_raw = c->d_vpls; A->vg_start = c->d_vlp_cell_start; A->vg_refs = c->d_vlp_refs;
+        for (int a = 0; a < 3; ++a) { A->vg_bmin[a] = c->vlp_grid_desc.box_min[a]; A->vg_cell[a] = c->vlp_grid_desc.cell_size[a]; A->vg_res[a] = c->vlp_grid_desc.res[a]; }
+    }
     return 0;
 }
 
@@ -730,7 +737,7 @@ static pt_render_params resolve_auto(pt_ctx c, const pt_render_params *in, const
     const int nrows = A.nrows;
     pt_render_params p = *in;
     if (p.kernel == PT_KERNEL_AUTO) {
-        if (p.variant == PT_VARIANT_BIDIR) p.kernel = PT_KERNEL_MEGA;
+        if (p.variant == PT_VARIANT_BIDIR || p.variant == PT_VARIANT_VLPGRID) p.kernel = PT_KERNEL_MEGA;
         else if (p.variant == PT_VARIANT_NODOF) p.kernel = PT_KERNEL_MEGA;   // single-copy Sample(): 0.433 ms vs 0.479 ms persistent (512x512)
         else if (p.variant == PT_VARIANT_GRID) p.kernel = PT_KERNEL_MEGA;
         else {
@@ -758,8 +765,8 @@ static int dispatch(pt_ctx c, const pt_render_params *pin, const pt::LaunchArgs 
     DevLock lock(c->device);     // constant-scene bind + launch are one critical section per device
     PT_CUDA(cudaMemsetAsync(c->d_counters, 0, 8 * sizeof(unsigned long long), c->stream), "clear counters");
     if (A.nrows <= 0) return 0;
-    if (p->variant == PT_VARIANT_BIDIR) {
-        if (p->kernel != PT_KERNEL_MEGA) return pt_fail(1, "render: the bidirectional variant has the megakernel flavour only (PT_KERNEL_MEGA / AUTO)");
+    if (p->variant == PT_VARIANT_BIDIR || p->variant == PT_VARIANT_VLPGRID) {
+        if (p->kernel != PT_KERNEL_MEGA) return pt_fail(1, "render: the bidirectional variants have the megakernel flavour only (PT_KERNEL_MEGA / AUTO)");
         return pt_launch_bidir(c, p, A);
     }
     switch (p->kernel) {
@@ -853,6 +860,7 @@ extern "C" pt_event pt_launch_lighttracer(pt_ctx c, int n_vlp_per_light, const u
     }
     cudaEventRecord(e->stop, c->stream);
     c->nvpl = n_vlp_per_light * nl;
+    c->vlp_grid_set = false;          // a VLP grid built on the previous buffer is stale
     c->vpls_set = true;
     return e;
 }
@@ -867,6 +875,7 @@ extern "C" int pt_set_vpls(pt_ctx c, const float *vpls, int n) {
     PT_CUDA(cudaGetLastError(), "launch k_compact_vpls");
     PT_CUDA(cudaStreamSynchronize(c->stream), "sync VPL upload");     // the host buffer may be pageable
     c->nvpl = n;
+    c->vlp_grid_set = false;          // a VLP grid built on the previous buffer is stale
     c->vpls_set = true;
     return 0;
 }
@@ -1150,6 +1159,8 @@ extern "C" int pt_render_host(pt_ctx c, const pt_scene *scene, const pt_grid *gr
         if (!g) return 1;
         pt_release_event(g);
     }
+    if (p->variant == PT_VARIANT_VLPGRID)
+        return pt_fail(1, "pt_render_host: the vlpgrid variant needs its VPL buffer and VLP grid set up explicitly (pt_set_vpls / pt_launch_lighttracer, pt_vlp_bounds, pt_build_vlp_grid, then pt_launch_pathtracer)");
     if (p->variant == PT_VARIANT_BIDIR) {
         pt_event l = pt_launch_lighttracer(c, p->n_vlp > 0 ? p->n_vlp : 512, p->seeds, p->arith);
         if (!l) return 1;

@@ -141,6 +141,7 @@ typedef struct {
     V3 box_min, box_max; int res[3]; V3 cell;
     const uint32_t *cell_start, *cell_refs;
     int bidir; const float *vpls; int nvpl;
+    int vlpgrid;             /* bidir Sample with the VLP-grid gather (vlpgrid:323-348); the grid is in box_min/res/cell/cell_start/cell_refs */
 } Scene;
 
 /* base:111-134 / grid:61-85 — Moller-Trumbore on one triangle; returns 1 if *t improved */
@@ -268,6 +269,28 @@ static inline V3 sample(const Scene *S, V3 o, V3 d, Rng *rng, oracle_counters *c
     V3 X = vmadd(d, t, o);
     float illum = 0.0f;
     if (S->bidir) {
+      if (S->vlpgrid) {
+        /* vlpgrid:323-348 — the VPLs of the cell that contains the hit point.  convert_int4 truncates (and saturates); the
+         * linear index is formed WITHOUT per-axis range checks (:325-326), so a point outside the box can alias into a cell */
+        const int ix = f2i_rz_sat((X.x - S->box_min.x) / S->cell.x), iy = f2i_rz_sat((X.y - S->box_min.y) / S->cell.y),
+                  iz = f2i_rz_sat((X.z - S->box_min.z) / S->cell.z);
+        const uint32_t rx = (uint32_t)S->res[0], ry = (uint32_t)S->res[1], rz = (uint32_t)S->res[2];
+        const int32_t index = (int32_t)((uint32_t)iz * rx * ry + (uint32_t)iy * rx + (uint32_t)ix);
+        if (index >= 0 && index < (int32_t)(rx * ry * rz)) {
+            for (uint32_t k = S->cell_start[index]; k < S->cell_start[index + 1]; ++k) {
+                const float *P = S->vpls + 4 * (size_t)S->cell_refs[k];
+                float I = P[3];
+                V3 dv = vsub(v3(P[0], P[1], P[2]), X);
+                float dist = sqrtf(dot3(dv, dv));
+                V3 ld = v3(dv.x / dist, dv.y / dist, dv.z / dist);
+                float lam = dot3(ld, n);
+                if (lam < 0.0f) continue;
+                float f = I / (dist * dist);
+                f = 1.0f < f ? 1.0f : f;
+                illum = MADD(lam, f, illum);
+            }
+        }
+      } else {
         /* bidir:165-187 — every VPL, unshadowed */
         for (int i = 0; i < S->nvpl; ++i) {
             const float *P = S->vpls + 4 * (size_t)i;
@@ -282,6 +305,7 @@ static inline V3 sample(const Scene *S, V3 o, V3 d, Rng *rng, oracle_counters *c
             f = 1.0f < f ? 1.0f : f;
             illum = MADD(lam, f, illum);
         }
+      }
         if (illum > 1.0f) illum = 1.0f;
         /* bidir:190-201 — soft shadows: each occluded real light SUBTRACTS 1/nlights; the shadow ray is bounded by
          * the un-jittered distance to the light (t = distanceFromLight, TraceRay keeps the running bound) */
@@ -361,7 +385,8 @@ static void scene_from_job(const oracle_job *J, Scene *S) {
     S->res[0] = J->grid_res[0]; S->res[1] = J->grid_res[1]; S->res[2] = J->grid_res[2];
     S->cell = v3(J->cell_size[0], J->cell_size[1], J->cell_size[2]);
     S->cell_start = J->cell_start; S->cell_refs = J->cell_refs;
-    S->bidir = J->variant == ORACLE_BIDIR;
+    S->bidir = J->variant == ORACLE_BIDIR || J->variant == ORACLE_VLPGRID;
+    S->vlpgrid = J->variant == ORACLE_VLPGRID;
     S->vpls = J->vpls; S->nvpl = J->nvpl;
 }
 
@@ -433,8 +458,9 @@ static int g_threads_used = 0;
 int oracle_threads_used(void) { return g_threads_used; }
 
 int oracle_render(const oracle_job *J, uint8_t *rgba8, float *accum, uint32_t *rng_state, oracle_counters *counters) {
-    if (!J || J->width <= 0 || J->height <= 0 || J->spp <= 0 || J->variant < 0 || J->variant > 4) return -1;
-    if (J->variant == ORACLE_BIDIR && (J->nvpl < 0 || (J->nvpl > 0 && !J->vpls))) return -1;
+    if (!J || J->width <= 0 || J->height <= 0 || J->spp <= 0 || J->variant < 0 || J->variant > 5) return -1;
+    if ((J->variant == ORACLE_BIDIR || J->variant == ORACLE_VLPGRID) && (J->nvpl < 0 || (J->nvpl > 0 && !J->vpls))) return -1;
+    if (J->variant == ORACLE_VLPGRID && (!J->cell_start || !J->cell_refs)) return -1;
     if (J->variant == ORACLE_NODOF && J->spp != 64) return -1;
     if (J->variant == ORACLE_GRID && (!J->cell_start || (!J->cell_refs && J->ntriangles > 0))) return -1;
     Scene S;

@@ -19,6 +19,11 @@
  *   3 grid   CLSuperPathTracer_trianglegrid/ lmem semantics, triangles through the uniform grid (DDA)
  *   4 bidir  CLSuperBidirectionalPathTracer/ lmem TraceRay; lightTracer kernel deposits virtual point lights
  *            (VPLs), Sample gathers all of them unshadowed, then SUBTRACTS 1/nlights per occluded real light
+ *   5 vlpgrid  kernel pathTracer of CLSuperMetropolisPathTracer_vlpgrid/metropolispathtracer.ocl:649-684 with its Sample
+ *            (:296-386): the bidir Sample, except that the gather visits only the VPLs listed in the VLP-grid cell that
+ *            contains the hit point (no zero-intensity skip, linear cell index without per-axis range checks).  The VPL
+ *            buffer (vpls/nvpl) and the VLP grid (box_min, grid_res, cell_size, cell_start/cell_refs in CSR form, lists in
+ *            ascending light order, <= 62 per cell) are inputs.
  *
  * Arithmetic policy (compile-time PT_CONTRACT):
  *   0  every float operation individually rounded (what g++ makes of the reference .ocl; image bytes
@@ -38,7 +43,7 @@
 extern "C" {
 #endif
 
-enum { ORACLE_BASE = 0, ORACLE_LMEM = 1, ORACLE_NODOF = 2, ORACLE_GRID = 3, ORACLE_BIDIR = 4 };
+enum { ORACLE_BASE = 0, ORACLE_LMEM = 1, ORACLE_NODOF = 2, ORACLE_GRID = 3, ORACLE_BIDIR = 4, ORACLE_VLPGRID = 5 };
 
 typedef struct {
     uint64_t samples;        /* Sample() calls                         */

@@ -14,7 +14,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 BUILD = os.path.join(HERE, "_build")
-VARIANTS = {"base": 0, "lmem": 1, "nodof": 2, "grid": 3, "bidir": 4}
+VARIANTS = {"base": 0, "lmem": 1, "nodof": 2, "grid": 3, "bidir": 4, "vlpgrid": 5}
 
 
 def build(force=False):
@@ -212,7 +212,7 @@ class OracleLib:
         if rows is not None:
             J.row_begin, J.row_end = rows
         tris = self._fill_scene(J, seeds, scene)
-        if variant == "bidir":
+        if variant in ("bidir", "vlpgrid"):
             if vpls is None:
                 vpls = self.light_tracer(seeds, scene, n_vlp)
             vpls = np.ascontiguousarray(vpls, np.float32).reshape(-1, 4)
@@ -221,6 +221,21 @@ class OracleLib:
         cam = cam or self.camera()
         J.cam_up[:] = list(cam["cam_up"]); J.cam_right[:] = list(cam["cam_right"]); J.eye_offset[:] = list(cam["eye_offset"])
         keep = None
+        if variant == "vlpgrid":
+            # `grid`: the VLP grid {"box_min", "res", "cell_size", "csr": (start, refs)}; None builds it as the reference host
+            # would (bounds of the buffer, its grid formula with `modifier`, initVLPsGrid)
+            if grid is None:
+                lo, hi = self.vlp_bounds(vpls)
+                res, cell = self.grid_dims(lo, hi, vpls.shape[0], modifier)
+                grid = {"box_min": lo, "res": res, "cell_size": cell, "csr": self.build_vlp_grid(vpls, lo, res, cell)}
+            start, refs = grid["csr"]
+            if refs.size == 0:
+                refs = np.zeros(1, np.uint32)
+            keep = (start, refs)
+            J.box_min[:] = [float(x) for x in grid["box_min"]]
+            J.grid_res[:] = [int(x) for x in grid["res"]]; J.cell_size[:] = [float(x) for x in grid["cell_size"]]
+            J.cell_start = start.ctypes.data_as(C.POINTER(C.c_uint32))
+            J.cell_refs = refs.ctypes.data_as(C.POINTER(C.c_uint32))
         if variant == "grid":
             if grid is None:
                 res, cell = self.grid_dims(scene["box_min"], scene["box_max"], tris.shape[0], modifier)
@@ -249,6 +264,8 @@ class OracleLib:
             raise ValueError("oracle_render rejected the job")
         del keep
         out = {"image": img, "accum": acc, "rng_state": rng, "counters": cnt.as_dict(), "threads": int(self.lib.oracle_threads_used())}
-        if variant == "bidir":
+        if variant in ("bidir", "vlpgrid"):
             out["vpls"] = vpls
+        if variant == "vlpgrid":
+            out["vlp_grid"] = grid
         return out

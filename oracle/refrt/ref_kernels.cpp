@@ -8,7 +8,7 @@
  *   REF_VARIANT 2  CLSuperPathTracer_lmem_NoDoF/pathtracer.ocl   (nodof)
  *   REF_VARIANT 3  CLSuperPathTracer_trianglegrid/pathtracer.ocl (grid)
  *   REF_VARIANT 4  CLSuperBidirectionalPathTracer/bidirectionalpathtracer.ocl (bidir)
- *   REF_VARIANT 5  CLSuperMetropolisPathTracer_vlpgrid/metropolispathtracer.ocl (VLP bounding box + VLP grid kernels only)
+ *   REF_VARIANT 5  CLSuperMetropolisPathTracer_vlpgrid/metropolispathtracer.ocl (VLP bounding box, VLP grid and pathTracer kernels)
  *
  * REF_OCL_GEN is the reference source with vector literals rewritten by ocl2cpp.py; the Makefile
  * pipes it in ("/dev/stdin"), so no copy of it is written anywhere.  Argument
@@ -113,8 +113,16 @@ const RefKernelDesc ref_kernel_table[] = {
     {"pathTracer", 18, tramp_pathTracer}, {"lightTracer", 12, tramp_lightTracer}, {nullptr, 0, nullptr}};
 #elif REF_VARIANT == 5
 /* CLSuperMetropolisPathTracer_vlpgrid/metropolispathtracer.ocl: only the kernels that are pure functions of a VLP buffer
- * are registered (argument order: CLSuperMetropolisPathTracer.c:262-296 reduction(), :298-321 initVLPsGrid()); the
- * Metropolis light tracer and the path tracer of that program are compiled but not exposed. */
+ * are registered (argument order: CLSuperMetropolisPathTracer.c:262-296 reduction(), :298-321 initVLPsGrid(), :186-227
+ * pathTracer() — a function of scene + VLP buffer + VLP grid); the Metropolis light tracer of that program is compiled
+ * but not exposed. */
+static void tramp_pathTracer(const RefLaunch &L) {
+    ocl::pathTracer((uchar4 *)L.mem(0), (const int *)L.mem(1), (const int *)L.mem(2), (const Triangle *)L.mem(3), L.val<int>(4),
+                    (const float4 *)L.mem(5), L.val<int>(6), (const Cell *)L.mem(7), L.val<float4>(8), L.val<float4>(9),
+                    L.val<int4>(10), (const float4 *)L.mem(11), L.val<int>(12), L.val<float4>(13), L.val<float4>(14),
+                    L.val<float4>(15), L.val<float4>(16), seeds_arg(L, 17), (int *)L.local(18), (int *)L.local(19),
+                    (float4 *)L.local(20));
+}
 static void tramp_reduce_minmax(const RefLaunch &L) {
     ocl::reduceMinAndMax_lmem((float4 *)L.mem(0), (float8 *)L.mem(1), (float8 *)L.local(2), L.val<int>(3));
 }
@@ -127,6 +135,7 @@ static void tramp_init_vlps_grid(const RefLaunch &L) {
 const RefKernelDesc ref_kernel_table[] = {{"reduceMinAndMax_lmem", 4, tramp_reduce_minmax},
                                           {"reduceMinAndMax_lmem_nwg", 4, tramp_reduce_minmax_nwg},
                                           {"initVLPsGrid", 5, tramp_init_vlps_grid},
+                                          {"pathTracer", 21, tramp_pathTracer},
                                           {nullptr, 0, nullptr}};
 #else
 #error "REF_VARIANT must be 0..5"

@@ -8,6 +8,8 @@ and kernels compiled by `make -C oracle ref` (oracle/refrt).  Only runnable in t
   golden_host.json     what the reference hosts print: camera, counts, bbox, grid size; PAM header bytes
   golden_images.npz    result.ppm of every variant for two seed sets at 512x512: SHA-256 + selected rows
   golden_grid.npz      cell contents (sorted ids) written by the reference's initTrianglesGrid kernel
+  golden_vlpgrid.npz   CLSuperMetropolisPathTracer_vlpgrid: VLP bounding box, VLP grid cells and frames of its pathTracer kernel
+                       (injected VPL buffers + grid), all from the reference's own kernels
   golden_bidir.npz     CLSuperBidirectionalPathTracer: the VPL buffer its lightTracer kernel writes (bit patterns,
                        several N_VLP), result.ppm SHA-256 + rows, and what the host prints
 """
@@ -30,6 +32,8 @@ import write_scenes  # noqa: E402
 REF = os.path.join(ROOT, "oracle", "_ref")
 SEED_SETS = [(1, 2, 3, 4), (123456789, 42, 7, 99999)]
 ROWS = [100, 120, 250, 300, 350, 400, 511]
+FRAME_VLPGRID = (256, 192)                      # frames of the vlpgrid program's pathTracer kernel
+FRAME_VLPGRID_ROWS = [40, 60, 80, 100, 130, 160, 191]
 
 
 def lib(variant):
@@ -171,6 +175,20 @@ def grid_golden(tmp):
             n = min(int(nels[c]), 62)
             srt[c, :n] = np.sort(ids[c, :n])
         out[name + "_res"] = res; out[name + "_cell"] = cell.view(np.uint32); out[name + "_nels"] = nels; out[name + "_ids"] = srt
+        # frames of the reference's own pathTracer kernel on this buffer and on the grid in its DEFINED form (ascending ids:
+        # the atomic_inc arrival order of initVLPsGrid is not part of the program's meaning): full SHA-256 + selected rows
+        if name in ("bidir", "synthetic"):
+            cb = np.zeros((ncells, 128), np.uint8)
+            cb[:, :4] = nels.astype(np.uint32).reshape(-1, 1).view(np.uint8)
+            ids_clean = np.where(srt == 65535, 0, srt).astype(np.uint16)
+            cb[:, 4:] = ids_clean.view(np.uint8).reshape(ncells, 124)
+            cam = o.camera()
+            for si, seeds in enumerate(SEED_SETS):
+                W, H = FRAME_VLPGRID
+                img = ref_vlpgrid_pathtracer(L, sc, cam, seeds, W, H, vpl, np.ascontiguousarray(cb.reshape(-1)), vmin, res, cell)
+                key = "%s_frame_s%d" % (name, si)
+                out[key + "_sha256"] = np.frombuffer(hashlib.sha256(img.tobytes()).digest(), np.uint8)
+                out[key + "_rows"] = img[FRAME_VLPGRID_ROWS]
         out[name + "_modifier"] = np.float32(modifier)
     np.savez_compressed(os.path.join(HERE, "golden_grid.npz"), **out)
 
@@ -234,6 +252,38 @@ def bidir_golden(tmp):
     out["rows"] = np.array(ROWS)
     out["host_json"] = np.frombuffer(json.dumps(host).encode(), np.uint8)
     np.savez_compressed(os.path.join(HERE, "golden_bidir.npz"), **out)
+
+
+def ref_vlpgrid_pathtracer(L, sc, cam, seeds, W, H, vpl, cells_bytes, vmin, res, cell):
+    """Kernel pathTracer of CLSuperMetropolisPathTracer_vlpgrid (metropolispathtracer.ocl:649-684) through refrt's CL entry
+    points, argument order of CLSuperMetropolisPathTracer.c:324-392, on an injected VPL buffer and VLP grid -> (H, W, 4) uint8."""
+    for fn in ("clCreateKernel", "clCreateBuffer", "clEnqueueMapBuffer"):
+        getattr(L, fn).restype = C.c_void_p
+    err = C.c_int()
+    k = C.c_void_p(L.clCreateKernel(None, b"pathTracer", C.byref(err)))
+    COPY = C.c_uint64(1 << 5)
+
+    def buf(a):
+        return C.c_void_p(L.clCreateBuffer(None, COPY, C.c_size_t(a.nbytes), a.ctypes.data_as(C.c_void_p), C.byref(err)))
+    sph = np.ascontiguousarray(sc["spheres"], np.int32); sq = np.ascontiguousarray(sc["squares"], np.int32)
+    tris = np.ascontiguousarray(sc["triangles"], np.float32); lights = np.ascontiguousarray(sc["lights"], np.float32)
+    nl = lights.shape[0]
+    img = np.zeros((H, W, 4), np.uint8)
+    vpl = np.ascontiguousarray(vpl, np.float32).reshape(-1, 4)
+    bi, bs, bq, bt, bv, bc, bl = buf(img), buf(sph), buf(sq), buf(tris), buf(vpl), buf(cells_bytes), buf(lights)
+    ntri = C.c_int32(tris.shape[0]); nv = C.c_int32(vpl.shape[0]); nlc = C.c_int32(nl); sd = (C.c_uint32 * 4)(*seeds)
+    f4 = lambda v: (C.c_float * 4)(*[float(x) for x in v])
+    r4 = (C.c_int32 * 4)(*[int(x) for x in res])
+    args = [(8, C.byref(bi)), (8, C.byref(bs)), (8, C.byref(bq)), (8, C.byref(bt)), (4, C.byref(ntri)), (8, C.byref(bv)), (4, C.byref(nv)),
+            (8, C.byref(bc)), (16, f4(vmin)), (16, f4(cell)), (16, r4), (8, C.byref(bl)), (4, C.byref(nlc)),
+            (16, f4(cam["cam_forward"])), (16, f4(cam["cam_up"])), (16, f4(cam["cam_right"])), (16, f4(cam["eye_offset"])), (16, sd),
+            (36, None), (36, None), (16 * nl, None)]
+    for i, (size, ptr) in enumerate(args):
+        assert L.clSetKernelArg(k, i, C.c_size_t(size), ptr) == 0, i
+    gws = (C.c_size_t * 2)(W, H)
+    assert L.clEnqueueNDRangeKernel(None, k, 2, None, gws, None, 0, None, None) == 0
+    ptr = L.clEnqueueMapBuffer(None, bi, 1, 1, C.c_size_t(0), C.c_size_t(img.nbytes), 0, None, None, C.byref(err))
+    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(H, W, 4)).copy()
 
 
 def vlpgrid_golden(tmp):
@@ -302,6 +352,20 @@ def vlpgrid_golden(tmp):
             m = min(int(nels[c]), 62)
             srt[c, :m] = np.sort(ids[c, :m])
         out[name + "_res"] = res; out[name + "_cell"] = cell.view(np.uint32); out[name + "_nels"] = nels; out[name + "_ids"] = srt
+        # frames of the reference's own pathTracer kernel on this buffer and on the grid in its DEFINED form (ascending ids:
+        # the atomic_inc arrival order of initVLPsGrid is not part of the program's meaning): full SHA-256 + selected rows
+        if name in ("bidir", "synthetic"):
+            cb = np.zeros((ncells, 128), np.uint8)
+            cb[:, :4] = nels.astype(np.uint32).reshape(-1, 1).view(np.uint8)
+            ids_clean = np.where(srt == 65535, 0, srt).astype(np.uint16)
+            cb[:, 4:] = ids_clean.view(np.uint8).reshape(ncells, 124)
+            cam = o.camera()
+            for si, seeds in enumerate(SEED_SETS):
+                W, H = FRAME_VLPGRID
+                img = ref_vlpgrid_pathtracer(L, sc, cam, seeds, W, H, vpl, np.ascontiguousarray(cb.reshape(-1)), vmin, res, cell)
+                key = "%s_frame_s%d" % (name, si)
+                out[key + "_sha256"] = np.frombuffer(hashlib.sha256(img.tobytes()).digest(), np.uint8)
+                out[key + "_rows"] = img[FRAME_VLPGRID_ROWS]
     np.savez_compressed(os.path.join(HERE, "golden_vlpgrid.npz"), **out)
 
 
