@@ -18,6 +18,11 @@
 
 #include "pt_host.h"
 
+// 1: the big-grid megakernel inlines TraceRay twice (sample_two_traces).  Round 1 measured that form faster at the 64-register budget
+// (4.57 vs 4.77 ms per 4 spp); with the leaner grid walk of round 2 the single ray loop wins (12.29 vs 12.57 ms per 16 spp).
+#ifndef PT_BIG_TWO_TRACES
+#define PT_BIG_TWO_TRACES 0
+#endif
 namespace pt {
 
 __constant__ SceneBlock c_scene;
@@ -116,7 +121,7 @@ __global__ void __launch_bounds__(128, (BIG && VARIANT == PT_VARIANT_GRID) ? 8 :
         for (int s = 0; s < P.spp; ++s) {
             V3 o, d;
             camera_ray<FMA>(P.cam, rng, i, j, o, d);
-            V3 c = (BIG && GRID) ? sample_two_traces<FMA, CARRY, GRID>(P.ap, S, P.grid, o, d, rng, cnt)
+            V3 c = (BIG && GRID && PT_BIG_TWO_TRACES) ? sample_two_traces<FMA, CARRY, GRID>(P.ap, S, P.grid, o, d, rng, cnt)
                                  : sample<FMA, CARRY, GRID, BIG && !GRID>(P.ap, S, P.grid, o, d, rng, cnt);
             cx = Ar<FMA>::madd(c.x, P.scale, cx);
             cy = Ar<FMA>::madd(c.y, P.scale, cy);
