@@ -87,8 +87,8 @@ PT_DEV void flush_counters(const LaunchArgs &P, const Counters &c, int ntri_coun
     }
 }
 
-// BIG, trianglegrid: grids whose records do not stay in L1 — 64 registers / 8 CTAs per SM and the two-trace form of
-// Sample(); otherwise 80 registers / 6 CTAs and the single ray loop (smaller code, instruction-cache resident).
+// BIG, trianglegrid: grids whose records do not stay in L1 — 64 registers / 8 CTAs per SM (72 / 7: 14.78 vs 14.51 ms per 16 spp)
+// and the longest-tile-first launch order; otherwise 80 registers / 6 CTAs.  Both use the single ray loop (PT_BIG_TWO_TRACES).
 // BIG, brute-force variants: frames above 400 k pixels — per-cluster triangle culling compiled in (tri_loop<.., CL>).
 // Measured (B200): soup 1 M triangles 4.57 ms per 4 spp with BIG vs 4.87 without; default 96-triangle grid scene
 // 1.41 ms without vs 1.58 with.

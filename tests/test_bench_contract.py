@@ -73,3 +73,29 @@ def test_committed_bench_lines_follow_the_contract():
         assert not set(j["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}, f
         assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(j["roofline"]), f
         assert "workload" in j["config"] and "l2" in j["config"], f
+
+
+def test_committed_round2_lines_headline_config4_parity_and_ray_accounting():
+    """round 2: headline = BASELINE config 4 at N = 1, config 5 strong-scaled at N > 1; every line checked what it timed
+    (bit-exact row bands vs the oracle, reduced frame == one-GPU frame) and says how rays are counted."""
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r2_4[0-9]_bench_n*.json")) + glob.glob(os.path.join(ROOT, "profiles", "r2_37_bench_n1.json")))
+    assert len(files) >= 3
+    for f in files:
+        j = json.loads(open(f).read().strip().splitlines()[-1])
+        assert BASE_KEYS <= set(j), f
+        n = j["n_gpus"]
+        assert j["config"]["workload"] == ("gridsoup1m_1920x1080x256" if n == 1 else "gridsoup1m_3840x2160x64"), f
+        assert j["scaling"] == ("weak" if n == 1 else "strong"), f
+        assert j["parity_check"]["bit_exact"] is True and j["parity_check"]["mismatching_pixels"] == 0, f
+        if n > 1:
+            assert j["parity_check"]["multi_gpu"]["identical"] is True, f
+            assert len(j["per_rank"]["render_kernel_ms"]["per_rank"]) == n, f
+        # rays: the reference's TraceRay calls; the elided dead shadow rays are reported, not hidden
+        assert 0 < j["rays_traced_per_step"] < j["rays_per_step"] and "TraceRay calls of the REFERENCE" in j["ray_count"], f
+        assert abs(j["value"] - j["rays_per_step"] / 1e3 / j["ms_per_step"]) < 1e-6 * j["value"], f
+        assert j["roofline"]["bound"] == "fp32" and 0 < j["roofline"]["frac"] < 1 and j["roofline"]["peak"] > 60, f
+        assert not set(j["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}, f
+        if n == 1 and "configs" in j:
+            for name, c in j["configs"].items():
+                assert c["parity_check"]["bit_exact"] is True, (f, name)
+                assert c["cpu_baseline"]["value"] > 0 and c["e2e"]["ms_per_step"] >= c["ms_per_step"], (f, name)
