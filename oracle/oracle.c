@@ -448,6 +448,195 @@ int oracle_light_tracer(const oracle_job *J, int n, float *vpl_out, uint32_t *rn
     return 0;
 }
 
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * CLSuperMetropolisPathTracer(_vlpgrid)/metropolispathtracer.ocl in FIX mode: kernels lightTracer (seed paths, :430-468 of
+ * the plain program / vlpgrid:502-536) and MetropolisLightTracer (:470-531 / vlpgrid:538-...), with VerifyIntersection's
+ * uninitialised hit bound replaced by the default distance 1e9 (the one-line patch oracle/Makefile applies to the reference
+ * for libref_vlpgrid_fix.so) and the seed paths in their own buffer (the reference host hands lightTracer the VPL buffer).
+ * Everything else is restated as written — including that every helper takes the RNG state BY VALUE (:146,159,172,184,241),
+ * so a work-item's "random" directions repeat: GetRandomPath shoots its four segments along one direction, every mutation
+ * round draws the same numbers. */
+typedef struct { V3 v[4]; uint32_t length; } MPath;
+
+/* :146-156 — rng by value: the caller's state is untouched */
+static inline V3 metro_random_direction(Rng rng) {
+    float r0 = 0.0f, r1 = 0.0f, sum = 2.0f;
+    while (sum >= 1.0f) {
+        rng_next_pm1(&rng, &r0, &r1);
+        sum = MADD(r1, r1, r0 * r0);
+    }
+    float sq = sqrtf(1.0f - sum);
+    return v3((2.0f * r0) * sq, (2.0f * r1) * sq, 1.0f - 2.0f * sum);
+}
+
+/* :158-170 */
+static inline int metro_add_vertex(const Scene *S, V3 origin, V3 *vertex, MPath *path, Rng rng, oracle_counters *cnt) {
+    const V3 d = metro_random_direction(rng);
+    V3 n = v3(0, 0, 0);
+    float t = 1e9f;
+    if (trace_ray(S, origin, d, &t, &n, cnt)) {
+        *vertex = vmadd(d, t, origin);
+        path->length += 1;
+        return 1;
+    }
+    return 0;
+}
+
+/* :172-182 */
+static inline MPath metro_random_path(const Scene *S, V3 origin, Rng rng, oracle_counters *cnt) {
+    MPath p;
+    memset(&p, 0, sizeof(p));
+    V3 cur = origin;
+    for (int i = 0; i < 4; ++i) {
+        if (!metro_add_vertex(S, cur, &p.v[i], &p, rng, cnt)) break;
+        cur = p.v[i];
+    }
+    return p;
+}
+
+static inline float metro_perturb1(float vertex, float r, float dx) {
+    if (r < 0.5f) return vertex < 1.0f ? vertex + dx : vertex + dx - 1.0f;
+    return vertex < 0.0f ? vertex - dx + 1.0f : vertex - dx;
+}
+
+/* :184-221 — two RNG pairs (x, y from the first, z from the second), rng by value */
+static inline V3 metro_perturbation(V3 vertex, Rng rng) {
+    float a0, a1, b0, b1;
+    rng_next(&rng, &a0, &a1, NULL, NULL);
+    rng_next(&rng, &b0, &b1, NULL, NULL);
+    const float s1 = 1.0f / 512.0f, s2 = 1.0f / 16.0f;
+    const float q = s1 / s2, tail = s1 / (q + 1.0f);
+    const float dx = s1 / (q + fabsf(2.0f * a0 - 1.0f)) - tail;
+    const float dy = s1 / (q + fabsf(2.0f * a1 - 1.0f)) - tail;
+    const float dz = s1 / (q + fabsf(2.0f * b0 - 1.0f)) - tail;
+    return v3(metro_perturb1(vertex.x, a0, dx), metro_perturb1(vertex.y, a1, dy), metro_perturb1(vertex.z, b0, dz));
+}
+
+/* :223-236 with the FIX: t = 1e9 */
+static inline int metro_verify(const Scene *S, V3 origin, V3 dest, oracle_counters *cnt) {
+    float t = 1e9f;
+    V3 n = v3(0, 0, 0);
+    const V3 d = normalize3(vsub(dest, origin));
+    if (!trace_ray(S, origin, d, &t, &n, cnt)) return 0;
+    const V3 X = vmadd(d, t, origin);
+    return dest.x == X.x && dest.y == X.y && dest.z == X.z;
+}
+
+/* :238-294 */
+static inline void metro_mutate(const Scene *S, MPath *seed, V3 origin, Rng rng, oracle_counters *cnt) {
+    if (seed->length == 0) {
+        *seed = metro_random_path(S, origin, rng, cnt);
+        if (seed->length == 0) return;
+    }
+    float y0, y1;
+    rng_next(&rng, &y0, &y1, NULL, NULL);
+    const float prob = 1.0f / ((float)seed->length + 0.2f);
+    if (prob < y0) return;
+    MPath tmp;
+    memset(&tmp, 0, sizeof(tmp));
+    V3 cur = origin;
+    for (uint32_t i = 0; i < seed->length; ++i) {
+        tmp.v[i] = metro_perturbation(seed->v[i], rng);
+        if (metro_verify(S, cur, tmp.v[i], cnt)) { tmp.length++; cur = tmp.v[i]; }
+        else break;
+    }
+    if (tmp.length == seed->length) *seed = tmp;
+    if (seed->length == 1) {
+        if (y1 > 0.3f) { if (!metro_add_vertex(S, seed->v[0], &seed->v[1], seed, rng, cnt)) return; }
+        if (y1 > 0.7f) { if (!metro_add_vertex(S, seed->v[1], &seed->v[2], seed, rng, cnt)) return; }
+        if (y1 > 0.9f) metro_add_vertex(S, seed->v[2], &seed->v[3], seed, rng, cnt);
+    } else if (seed->length == 2) {
+        if (y1 < 0.3f) { if (!metro_add_vertex(S, seed->v[1], &seed->v[2], seed, rng, cnt)) return; }
+        if (y1 < 0.2f) metro_add_vertex(S, seed->v[2], &seed->v[3], seed, rng, cnt);
+    } else if (seed->length == 3) {
+        if (y1 < 0.2f) metro_add_vertex(S, seed->v[2], &seed->v[3], seed, rng, cnt);
+    }
+}
+
+/* :380-428 SampleFromLightSource of the Metropolis programs (constants 400 / 10 / 40, total_paths / 256) */
+static inline void metro_sample_from_light(const Scene *S, V3 o, V3 d, float I, int total_paths, float out[4], oracle_counters *cnt) {
+    float t = 1e9f;
+    V3 n = v3(0, 0, 0);
+    out[0] = out[1] = out[2] = out[3] = 0.0f;
+    int m = trace_ray(S, o, d, &t, &n, cnt);
+    if (!m) return;
+    V3 X = vmadd(d, t, o);
+    float lam = dot3(d, n);
+    if (lam < 0.0f) lam = 0.0f;
+    else {
+        V3 dv = vsub(o, X);
+        float dist = sqrtf(dot3(dv, dv));
+        float f = I / (dist * dist);
+        f = 1.0f < f ? 1.0f : f;
+        lam = lam * f;
+    }
+    if (lam > 1.0f) lam = 1.0f;
+    float k = m == 1 ? 400.0f : (m == 2 ? 10.0f : (m == 3 ? 40.0f : 0.0f));
+    if (k == 0.0f) return;
+    out[0] = X.x; out[1] = X.y; out[2] = X.z;
+    out[3] = (k * lam) / (float)(total_paths / 256);
+}
+
+/* paths_out (optional): n_paths*nlights x 20 words, the reference's Path layout {float4 v[4]; uint length; pad[3]} — only
+ * v[0..length) and length are defined.  vpl_out: 4*n_paths*nlights x 4 floats, entry 4*(gi + l*n_paths) + i. */
+int oracle_metropolis_light_tracer(const oracle_job *J, int n_paths, int mutation_rounds, uint32_t *paths_out, float *vpl_out) {
+    if (!J || n_paths <= 0 || mutation_rounds < 0 || !vpl_out || J->nlights < 0 || J->nlights > 5) return -1;
+    oracle_job Jl = *J;
+    Jl.variant = ORACLE_LMEM;
+    Scene S;
+    scene_from_job(&Jl, &S);
+    oracle_counters cnt;
+    memset(&cnt, 0, sizeof(cnt));
+    const int total_paths = n_paths * J->nlights;
+    for (int gi = 0; gi < n_paths; ++gi) {
+        const Rng rng = rng_seed(J->seeds, (uint32_t)gi);
+        for (int l = 0; l < J->nlights; ++l) {
+            V3 origin = v3(J->lights[l][0], J->lights[l][1], J->lights[l][2]);
+            const float I = J->lights[l][3];
+            MPath seed = metro_random_path(&S, origin, rng, &cnt);            /* kernel lightTracer */
+            if (paths_out) {
+                uint32_t *q = paths_out + 20 * ((size_t)gi + (size_t)l * n_paths);
+                memset(q, 0, 80);
+                for (uint32_t i = 0; i < seed.length; ++i) { memcpy(q + 4 * i, &seed.v[i], 12); }
+                q[16] = seed.length;
+            }
+            for (int m = 0; m < mutation_rounds; ++m) metro_mutate(&S, &seed, origin, rng, &cnt);   /* kernel MetropolisLightTracer */
+            float *out = vpl_out + 16 * ((size_t)gi + (size_t)l * n_paths);
+            memset(out, 0, 64);
+            for (uint32_t i = 0; i < seed.length; ++i) {
+                const V3 d = normalize3(vsub(seed.v[i], origin));
+                metro_sample_from_light(&S, origin, d, I / (float)(1 << i), total_paths, out + 4 * i, &cnt);
+                if (out[4 * i + 3] == 0.0f) break;
+                origin = seed.v[i];
+            }
+        }
+    }
+    return 0;
+}
+
+/* Mutate applied `rounds` times to one path (reference Path layout, 20 words), seeded as work-item gid: the counterpart of
+ * refrt's ref_probe_mutate — the kernel keeps the mutated path private, the probes make it comparable. */
+int oracle_metropolis_mutate(const oracle_job *J, uint32_t gid, const float origin[3], uint32_t path[20], int rounds) {
+    if (!J || !path || rounds < 0) return -1;
+    oracle_job Jl = *J;
+    Jl.variant = ORACLE_LMEM;
+    Scene S;
+    scene_from_job(&Jl, &S);
+    oracle_counters cnt;
+    memset(&cnt, 0, sizeof(cnt));
+    const Rng rng = rng_seed(J->seeds, gid);
+    MPath p;
+    memset(&p, 0, sizeof(p));
+    p.length = path[16];
+    if (p.length > 4) return -1;
+    for (uint32_t i = 0; i < 4; ++i) memcpy(&p.v[i], path + 4 * i, 12);
+    for (int m = 0; m < rounds; ++m) metro_mutate(&S, &p, v3(origin[0], origin[1], origin[2]), rng, &cnt);
+    for (uint32_t i = 0; i < 4; ++i) { memcpy(path + 4 * i, &p.v[i], 12); path[4 * i + 3] = 0; }
+    path[16] = p.length;
+    return 0;
+}
+
 static inline void cnt_add(oracle_counters *a, const oracle_counters *b) {
     a->samples += b->samples; a->rays += b->rays; a->shadow_rays += b->shadow_rays;
     a->tri_tests += b->tri_tests; a->cells_visited += b->cells_visited; a->prim_tests += b->prim_tests;

@@ -97,6 +97,13 @@ int oracle_threads_used(void);
 int oracle_light_tracer(const oracle_job *job, int n_vlp_per_light, float *vpl_out, uint32_t *rng_state,
                         oracle_counters *counters);
 
+/* Kernels lightTracer + MetropolisLightTracer of CLSuperMetropolisPathTracer(_vlpgrid)/metropolispathtracer.ocl in FIX mode
+ * (VerifyIntersection's uninitialised hit bound = 1e9, seed paths in their own buffer; see oracle.c).  paths_out (optional):
+ * n_paths*nlights x 20 words in the reference's Path layout; vpl_out: 4*n_paths*nlights x 4 floats.  0, or -1 on bad arguments. */
+int oracle_metropolis_light_tracer(const oracle_job *job, int n_paths, int mutation_rounds, uint32_t *paths_out, float *vpl_out);
+
+int oracle_metropolis_mutate(const oracle_job *job, uint32_t gid, const float origin[3], uint32_t path[20], int rounds);
+
 /* policy this library was built with (0 / 1) */
 int oracle_contract_mode(void);
 

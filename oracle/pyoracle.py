@@ -200,6 +200,29 @@ class OracleLib:
             raise ValueError("oracle_light_tracer rejected the job")
         return (vpl, rng) if want_rng else vpl
 
+    def metropolis_light_tracer(self, seeds, scene, n_paths=512, rounds=8):
+        """FIX-mode lightTracer + MetropolisLightTracer -> (seed paths (n*nl, 20) uint32, VPLs (4*n*nl, 4) float32)."""
+        J = oracle_job()
+        self._fill_scene(J, seeds, scene)
+        paths = np.zeros((n_paths * J.nlights, 20), np.uint32)
+        vpl = np.zeros((4 * n_paths * J.nlights, 4), np.float32)
+        self.lib.oracle_metropolis_light_tracer.restype = C.c_int
+        rc = self.lib.oracle_metropolis_light_tracer(C.byref(J), int(n_paths), int(rounds), paths.ctypes.data_as(C.c_void_p), vpl.ctypes.data_as(C.c_void_p))
+        if rc:
+            raise ValueError("oracle_metropolis_light_tracer rejected the job")
+        return paths, vpl
+
+    def metropolis_mutate(self, seeds, scene, gid, origin, path, rounds):
+        """Mutate x rounds on one path (20 uint32 words, the reference's Path layout) -> mutated path."""
+        J = oracle_job()
+        self._fill_scene(J, seeds, scene)
+        p = np.ascontiguousarray(path, np.uint32).copy()
+        o = (C.c_float * 3)(*[float(x) for x in origin])
+        self.lib.oracle_metropolis_mutate.restype = C.c_int
+        if self.lib.oracle_metropolis_mutate(C.byref(J), C.c_uint32(int(gid)), o, p.ctypes.data_as(C.c_void_p), int(rounds)):
+            raise ValueError("oracle_metropolis_mutate rejected the job")
+        return p
+
     def render(self, variant, width, height, seeds, scene, spp=64, rows=None, cam=None, grid=None, want_accum=True,
                want_rng=True, nthreads=0, modifier=3.0, vpls=None, n_vlp=512, sample_block=0, sample_blocks=0):
         """scene: dict with spheres, squares, triangles (n,12), lights (nl,4) [, box_min, box_max].

@@ -132,10 +132,27 @@ static void tramp_reduce_minmax_nwg(const RefLaunch &L) {
 static void tramp_init_vlps_grid(const RefLaunch &L) {
     ocl::initVLPsGrid((Cell *)L.mem(0), (const float4 *)L.mem(1), L.val<float4>(2), L.val<int4>(3), L.val<float4>(4));
 }
+#if defined(REF_METRO_FIX)
+/* FIX build only (oracle/Makefile: `float t = 1e9;` in VerifyIntersection): the seed-path tracer and the Metropolis light tracer,
+ * argument order of CLSuperMetropolisPathTracer_vlpgrid/CLSuperMetropolisPathTracer.c:186-260 */
+static void tramp_lightTracer(const RefLaunch &L) {
+    ocl::lightTracer((const int *)L.mem(0), (const int *)L.mem(1), (const Triangle *)L.mem(2), L.val<int>(3), (const float4 *)L.mem(4),
+                     L.val<int>(5), (Path *)L.mem(6), seeds_arg(L, 7), (int *)L.local(8), (int *)L.local(9), (float4 *)L.local(10));
+}
+static void tramp_metropolis(const RefLaunch &L) {
+    ocl::MetropolisLightTracer((const int *)L.mem(0), (const int *)L.mem(1), (const Triangle *)L.mem(2), L.val<int>(3),
+                               (const float4 *)L.mem(4), L.val<int>(5), (Path *)L.mem(6), (float16 *)L.mem(7), seeds_arg(L, 8),
+                               L.val<int>(9), (int *)L.local(10), (int *)L.local(11), (float4 *)L.local(12));
+}
+#endif
 const RefKernelDesc ref_kernel_table[] = {{"reduceMinAndMax_lmem", 4, tramp_reduce_minmax},
                                           {"reduceMinAndMax_lmem_nwg", 4, tramp_reduce_minmax_nwg},
                                           {"initVLPsGrid", 5, tramp_init_vlps_grid},
                                           {"pathTracer", 21, tramp_pathTracer},
+#if defined(REF_METRO_FIX)
+                                          {"lightTracer", 11, tramp_lightTracer},
+                                          {"MetropolisLightTracer", 13, tramp_metropolis},
+#endif
                                           {nullptr, 0, nullptr}};
 #else
 #error "REF_VARIANT must be 0..5"
@@ -184,6 +201,35 @@ int ref_probe_trace_ray(const float o[3], const float d[3], float *t_inout, floa
     int m = TraceRay(origin, dir, t_inout, &normal, sp, sq, tris.data(), ntris);
     n_out[0] = normal.x; n_out[1] = normal.y; n_out[2] = normal.z;
     return m;
+}
+#endif
+
+#if defined(REF_METRO_FIX)
+/* The reference's Mutate (metropolispathtracer.ocl:238-294; FIX build) applied `rounds` times to one path, seeded as work-item
+ * `gid` of the Metropolis kernels: the kernel itself keeps the mutated path in a private copy, so this is the only way to see it.
+ * path: the reference's Path layout, 20 words {float4 v[4]; uint length; pad}. */
+void ref_probe_mutate(const uint32_t seeds[4], uint32_t gid, const int32_t spheres[9], const int32_t squares[9], const float *tris12,
+                      int ntris, const float origin[3], uint32_t path[20], int rounds) {
+    size_t gsz[3] = {(size_t)gid + 1, 1, 1}, one[3] = {1, 1, 1};
+    WorkItem wi;
+    wi.gid[0] = gid; wi.gid[1] = 0; wi.gid[2] = 0;
+    wi.lid[0] = wi.lid[1] = wi.lid[2] = 0;
+    wi.grp[0] = gid; wi.grp[1] = wi.grp[2] = 0;
+    wi.gsz = gsz; wi.lsz = one; wi.ngrp = gsz;
+    WorkItem *saved = refrt_wi;
+    refrt_wi = &wi;
+    mwc64xvec2_state_t rng;
+    MWC64XVEC2_Seeding(&rng, uint4(seeds[0], seeds[1], seeds[2], seeds[3]));
+    int sp[9], sq[9];
+    for (int i = 0; i < 9; ++i) { sp[i] = spheres[i]; sq[i] = squares[i]; }
+    std::vector<Triangle> tris(ntris > 0 ? ntris : 1);
+    if (ntris > 0) std::memcpy((void *)tris.data(), tris12, sizeof(Triangle) * (size_t)ntris);
+    Path p;
+    std::memcpy((void *)&p, path, 80);
+    const float4 o(origin[0], origin[1], origin[2], 0.0f);
+    for (int m = 0; m < rounds; ++m) Mutate(&p, o, sp, sq, tris.data(), ntris, rng);
+    std::memcpy(path, (const void *)&p, 80);
+    refrt_wi = saved;
 }
 #endif
 

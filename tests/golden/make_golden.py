@@ -10,6 +10,8 @@ and kernels compiled by `make -C oracle ref` (oracle/refrt).  Only runnable in t
   golden_grid.npz      cell contents (sorted ids) written by the reference's initTrianglesGrid kernel
   golden_vlpgrid.npz   CLSuperMetropolisPathTracer_vlpgrid: VLP bounding box, VLP grid cells and frames of its pathTracer kernel
                        (injected VPL buffers + grid), all from the reference's own kernels
+  golden_metropolis.npz  seed paths and VPL buffers of lightTracer + MetropolisLightTracer in FIX mode (one-line patch, see
+                       oracle/Makefile) for several path counts / mutation rounds / seeds
   golden_bidir.npz     CLSuperBidirectionalPathTracer: the VPL buffer its lightTracer kernel writes (bit patterns,
                        several N_VLP), result.ppm SHA-256 + rows, and what the host prints
 """
@@ -32,6 +34,9 @@ import write_scenes  # noqa: E402
 REF = os.path.join(ROOT, "oracle", "_ref")
 SEED_SETS = [(1, 2, 3, 4), (123456789, 42, 7, 99999)]
 ROWS = [100, 120, 250, 300, 350, 400, 511]
+METRO_EXTRA_SEEDS = [(1, 0xC0000001, 3, 4), (5, 0xF0000000, 6, 7), (0xE0000000, 2, 3, 4), (0x40000000, 0x50000000, 9, 11),
+                     (0x26666666, 0xD9999999, 0, 0), (0x26666661, 0x59999999, 7, 5), (0x2666666F, 0x19999999, 1, 2)]   # first pair accepted, pointing down
+METRO_LIGHTS_BELOW = np.array([[9, 0.2, 1.0, 400], [3, -0.3, 2.0, 300], [12, 0.1, 0.5, 200]], np.float32)
 FRAME_VLPGRID = (256, 192)                      # frames of the vlpgrid program's pathTracer kernel
 FRAME_VLPGRID_ROWS = [40, 60, 80, 100, 130, 160, 191]
 
@@ -254,6 +259,110 @@ def bidir_golden(tmp):
     np.savez_compressed(os.path.join(HERE, "golden_bidir.npz"), **out)
 
 
+def ref_metropolis_vpls(L, sc, seeds, n_paths, rounds):
+    """FIX build of the reference (oracle/Makefile: `float t = 1e9;` in VerifyIntersection, nothing else): kernel lightTracer
+    writes the seed paths into ITS OWN buffer (the reference host hands it d_virtual_lights by mistake,
+    CLSuperMetropolisPathTracer.c:579), kernel MetropolisLightTracer mutates them `rounds` times and deposits 4 VPLs per path.
+    -> (seed paths as (n*nl, 20) uint32 words [4 x float4 + length + 3 pad], VPLs as (4*n*nl, 4) float32)."""
+    for fn in ("clCreateKernel", "clCreateBuffer", "clEnqueueMapBuffer"):
+        getattr(L, fn).restype = C.c_void_p
+    err = C.c_int()
+    COPY = C.c_uint64(1 << 5)
+
+    def buf(a):
+        return C.c_void_p(L.clCreateBuffer(None, COPY, C.c_size_t(a.nbytes), a.ctypes.data_as(C.c_void_p), C.byref(err)))
+    sph = np.ascontiguousarray(sc["spheres"], np.int32); sq = np.ascontiguousarray(sc["squares"], np.int32)
+    tris = np.ascontiguousarray(sc["triangles"], np.float32); lights = np.ascontiguousarray(sc["lights"], np.float32)
+    nl = lights.shape[0]
+    paths = np.zeros((n_paths * nl, 20), np.uint32)                 # sizeof(Path) = 80
+    vpl = np.full((n_paths * nl * 4, 4), np.nan, np.float32)
+    bs, bq, bt, bl, bp, bv = buf(sph), buf(sq), buf(tris), buf(lights), buf(paths), buf(vpl)
+    ntri = C.c_int32(tris.shape[0]); nlc = C.c_int32(nl); sd = (C.c_uint32 * 4)(*seeds); rd = C.c_int32(rounds)
+    k = C.c_void_p(L.clCreateKernel(None, b"lightTracer", C.byref(err)))
+    args = [(8, C.byref(bs)), (8, C.byref(bq)), (8, C.byref(bt)), (4, C.byref(ntri)), (8, C.byref(bl)), (4, C.byref(nlc)),
+            (8, C.byref(bp)), (16, sd), (36, None), (36, None), (16 * nl, None)]
+    for i, (size, ptr) in enumerate(args):
+        assert L.clSetKernelArg(k, i, C.c_size_t(size), ptr) == 0, i
+    gws = (C.c_size_t * 1)(n_paths)
+    assert L.clEnqueueNDRangeKernel(None, k, 1, None, gws, None, 0, None, None) == 0
+    ptr = L.clEnqueueMapBuffer(None, bp, 1, 1, C.c_size_t(0), C.c_size_t(paths.nbytes), 0, None, None, C.byref(err))
+    paths_out = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint32)), shape=paths.shape).copy()
+    k2 = C.c_void_p(L.clCreateKernel(None, b"MetropolisLightTracer", C.byref(err)))
+    args = [(8, C.byref(bs)), (8, C.byref(bq)), (8, C.byref(bt)), (4, C.byref(ntri)), (8, C.byref(bl)), (4, C.byref(nlc)),
+            (8, C.byref(bp)), (8, C.byref(bv)), (16, sd), (4, C.byref(rd)), (36, None), (36, None), (16 * nl, None)]
+    for i, (size, ptr) in enumerate(args):
+        assert L.clSetKernelArg(k2, i, C.c_size_t(size), ptr) == 0, i
+    assert L.clEnqueueNDRangeKernel(None, k2, 1, None, gws, None, 0, None, None) == 0
+    ptr = L.clEnqueueMapBuffer(None, bv, 1, 1, C.c_size_t(0), C.c_size_t(vpl.nbytes), 0, None, None, C.byref(err))
+    return paths_out, np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=vpl.shape).copy()
+
+
+def metropolis_golden(tmp):
+    """golden_metropolis.npz: seed paths and VPL buffers of the FIX-mode Metropolis kernels for several (paths, rounds, seeds)."""
+    from oracle.pyoracle import OracleLib
+    o = OracleLib(0)
+    d = os.path.join(tmp, "metro")
+    write_scenes.write_variant("bidir", d)
+    sc = o.load_scene_dir(d, "bidir")
+    L = lib("vlpgrid_fix")
+    env_seeds = os.environ.pop("PT_SEEDS", None)
+    out = {}
+    for si, seeds in enumerate(SEED_SETS):
+        for n_paths, rounds in ((512, 8), (512, 0), (300, 1), (128, 40)):
+            paths, vpl = ref_metropolis_vpls(L, sc, seeds, n_paths, rounds)
+            key = "s%d_n%d_r%d" % (si, n_paths, rounds)
+            out[key + "_paths"] = paths
+            out[key + "_vpl"] = vpl.view(np.uint32)
+    # a light list below the squares: their undersides face the lights, so many VPLs are non-zero and the mutation rounds
+    # (vertex additions along the second direction) change the buffer
+    sc2 = dict(sc, lights=METRO_LIGHTS_BELOW)
+    for n_paths, rounds in ((256, 0), (256, 8), (256, 3)):
+        paths, vpl = ref_metropolis_vpls(L, sc2, SEED_SETS[0], n_paths, rounds)
+        key = "below_n%d_r%d" % (n_paths, rounds)
+        out[key + "_paths"] = paths
+        out[key + "_vpl"] = vpl.view(np.uint32)
+    out["below_lights"] = METRO_LIGHTS_BELOW
+    # Mutate itself (the kernel keeps the mutated path private): the reference's function through ref_probe_mutate on the seed
+    # paths of 96 work-items x 2 lights, after 1, 2 and 8 rounds
+    paths0 = out["s0_n512_r0_paths"]
+    sph = np.ascontiguousarray(sc["spheres"], np.int32); sq = np.ascontiguousarray(sc["squares"], np.int32)
+    tris = np.ascontiguousarray(sc["triangles"], np.float32); lights = np.ascontiguousarray(sc["lights"], np.float32)
+    mut = {r: [] for r in (1, 2, 8)}
+    which = []
+    for gi in range(0, 512, 16):
+        for l in range(lights.shape[0]):
+            which.append((gi, l))
+            for r in mut:
+                p = paths0[gi + l * 512].copy()
+                L.ref_probe_mutate((C.c_uint32 * 4)(*SEED_SETS[0]), C.c_uint32(gi), sph.ctypes.data_as(C.c_void_p), sq.ctypes.data_as(C.c_void_p),
+                                   tris.ctypes.data_as(C.c_void_p), C.c_int(tris.shape[0]), (C.c_float * 3)(*lights[l, :3]),
+                                   p.ctypes.data_as(C.c_void_p), C.c_int(r))
+                mut[r].append(p)
+    out["mutate_which"] = np.array(which, np.int32)
+    for r in mut:
+        out["mutate_r%d" % r] = np.array(mut[r], np.uint32)
+    # The first RNG pair of EVERY work-item is (seeds.x ^ seeds.z, seeds.y ^ seeds.w) * 2^-32 (the seeding XORs one hash into all
+    # four words), and Mutate branches on it: with the host's 27-bit seeds it is always < 0.03125, so `y > 0.3 / 0.7 / 0.9` and
+    # `probability < x` never fire.  Seeds outside that range reach the other branches (the kernels take any uint4).
+    for ei, seeds in enumerate(METRO_EXTRA_SEEDS):
+        paths, vpl = ref_metropolis_vpls(L, sc, seeds, 256, 8)
+        out["extra%d_paths" % ei] = paths
+        out["extra%d_vpl" % ei] = vpl.view(np.uint32)
+        res = []
+        for gi in range(256):
+            for l in range(lights.shape[0]):
+                p = paths[gi + l * 256].copy()
+                L.ref_probe_mutate((C.c_uint32 * 4)(*seeds), C.c_uint32(gi), sph.ctypes.data_as(C.c_void_p), sq.ctypes.data_as(C.c_void_p),
+                                   tris.ctypes.data_as(C.c_void_p), C.c_int(tris.shape[0]), (C.c_float * 3)(*lights[l, :3]),
+                                   p.ctypes.data_as(C.c_void_p), C.c_int(8))
+                res.append(p)
+        out["extra%d_mutated" % ei] = np.array(res, np.uint32)
+    out["extra_seeds"] = np.array(METRO_EXTRA_SEEDS, np.uint32)
+    if env_seeds is not None:
+        os.environ["PT_SEEDS"] = env_seeds
+    np.savez_compressed(os.path.join(HERE, "golden_metropolis.npz"), **out)
+
+
 def ref_vlpgrid_pathtracer(L, sc, cam, seeds, W, H, vpl, cells_bytes, vmin, res, cell):
     """Kernel pathTracer of CLSuperMetropolisPathTracer_vlpgrid (metropolispathtracer.ocl:649-684) through refrt's CL entry
     points, argument order of CLSuperMetropolisPathTracer.c:324-392, on an injected VPL buffer and VLP grid -> (H, W, 4) uint8."""
@@ -379,10 +488,14 @@ if __name__ == "__main__":
         if sys.argv[1:] == ["vlpgrid"]:
             vlpgrid_golden(tmp)
             sys.exit(0)
+        if sys.argv[1:] == ["metropolis"]:
+            metropolis_golden(tmp)
+            sys.exit(0)
         rng_golden()
         trace_golden(tmp)
         images_and_host(tmp)
         grid_golden(tmp)
         bidir_golden(tmp)
         vlpgrid_golden(tmp)
+        metropolis_golden(tmp)
     print("golden vectors written to", HERE)
