@@ -122,6 +122,8 @@ PTCUDA_SYMBOLS = {
     "pt_read_rng_state": (_I, [_VP, _U32P, C.c_size_t]),
     "pt_get_counters": (_I, [_VP, C.POINTER(pt_counters)]),
     "pt_launch_lighttracer": (_VP, [_VP, _I, _U32P, _I]),
+    "pt_launch_metropolis_lighttracer": (_VP, [_VP, _I, _U32P, _I, _I]),
+    "pt_read_metropolis_paths": (_I, [_VP, _U32P, _I, _I]),
     "pt_set_vpls": (_I, [_VP, _FP, _I]),
     "pt_read_vpls": (_I, [_VP, _FP, _I]),
     "pt_render_device": (_I, [_VP, C.POINTER(pt_camera), C.POINTER(pt_render_params), _VP, _VP]),

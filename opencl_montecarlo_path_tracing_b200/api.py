@@ -276,6 +276,26 @@ class Renderer:
         self._l.pt_release_event(evt)
         return ms
 
+    def metropolis_light_tracer(self, seeds, n_paths=512, rounds=8, arith="fma"):
+        """Kernels lightTracer + MetropolisLightTracer of CLSuperMetropolisPathTracer(_vlpgrid) in FIX mode (include/ptcuda.h):
+        fills the context's VPL buffer with 4*n_paths*nlights entries.  Returns (seed paths (n*nl, 20) uint32, VPLs (4*n*nl, 4))."""
+        s = (C.c_uint32 * 4)(*[int(v) & 0xFFFFFFFF for v in seeds])
+        evt = self._l.pt_launch_metropolis_lighttracer(self.ctx, int(n_paths), s, int(rounds), PT_ARITH[arith])
+        if not evt:
+            raise PtError("pt_launch_metropolis_lighttracer failed: %s" % self._l.pt_last_error().decode())
+        _check(self._l.pt_wait(evt), "pt_wait")
+        self._l.pt_release_event(evt)
+        return self.read_metropolis_paths(mutated=False), self.read_vpls()
+
+    def read_metropolis_paths(self, mutated=False):
+        n = self._l.pt_read_metropolis_paths(self.ctx, None, 0, 0)
+        if n < 0:
+            raise PtError("pt_read_metropolis_paths failed: %s" % self._l.pt_last_error().decode())
+        p = np.zeros((max(n, 1), 20), np.uint32)
+        if self._l.pt_read_metropolis_paths(self.ctx, p.ctypes.data_as(C.POINTER(C.c_uint32)), max(n, 1), int(bool(mutated))) < 0:
+            raise PtError("pt_read_metropolis_paths failed: %s" % self._l.pt_last_error().decode())
+        return p[:n]
+
     def set_vpls(self, vpls):
         v = np.ascontiguousarray(vpls, np.float32).reshape(-1, 4)
         _check(self._l.pt_set_vpls(self.ctx, v.ctypes.data_as(C.POINTER(C.c_float)), v.shape[0]), "pt_set_vpls")

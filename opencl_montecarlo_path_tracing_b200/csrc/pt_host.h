@@ -112,6 +112,8 @@ struct pt_ctx_s {
     bool vpls_set;
     int nvpl;                     // entries of d_vpls (n_vlp_per_light * nlights)
     float4 *d_vpls, *d_vpl_active;
+    uint32_t *d_metro_seed, *d_metro_mutated;   // Metropolis FIX mode: seed paths / mutated paths, n_metro_paths x 20 words each
+    size_t metro_cap; int n_metro_paths;
     int *d_vpl_count;
     size_t vpls_cap;              // entries allocated
 

@@ -29,6 +29,7 @@
 #include "pt_spec.cuh"
 #include "pt_gridqueue.cuh"
 #include "pt_gridasync.cuh"
+#include "pt_metropolis.cuh"
 
 // ------------------------------------------------------------------------------------ errors
 static std::atomic<int> g_error_mode{PT_ERRORS_EXIT};
@@ -178,7 +179,7 @@ extern "C" void pt_destroy(pt_ctx c) {
     cudaFree(c->d_tile_order); cudaFree(c->d_cta_times);
     if (c->h_tile_order) cudaFreeHost(c->h_tile_order);
     if (c->h_cta_times) cudaFreeHost(c->h_cta_times);
-    cudaFree(c->d_vpls); cudaFree(c->d_vpl_active); cudaFree(c->d_vpl_count);
+    cudaFree(c->d_vpls); cudaFree(c->d_vpl_active); cudaFree(c->d_vpl_count); cudaFree(c->d_metro_seed); cudaFree(c->d_metro_mutated);
     cudaFree(c->d_vlp_keys); cudaFree(c->d_vlp_cell_start); cudaFree(c->d_vlp_refs);
     if (c->wf_exec) cudaGraphExecDestroy(c->wf_exec);
     free(c->wf_key_args);
@@ -863,6 +864,67 @@ extern "C" pt_event pt_launch_lighttracer(pt_ctx c, int n_vlp_per_light, const u
     c->vlp_grid_set = false;          // a VLP grid built on the previous buffer is stale
     c->vpls_set = true;
     return e;
+}
+
+// CLSuperMetropolisPathTracer(_vlpgrid): kernels lightTracer (seed paths) + MetropolisLightTracer, FIX mode (pt_metropolis.cuh)
+extern "C" pt_event pt_launch_metropolis_lighttracer(pt_ctx c, int n_paths_per_light, const uint32_t seeds[4], int mutation_rounds, int arith) {
+    if (!c || !seeds) { pt_fail(1, "pt_launch_metropolis_lighttracer: null argument"); return nullptr; }
+    if (!c->scene_set) { pt_fail(1, "pt_launch_metropolis_lighttracer: call pt_set_scene first"); return nullptr; }
+    if (n_paths_per_light <= 0 || (long long)n_paths_per_light * 20 > 0x7fffffffLL || mutation_rounds < 0) {
+        pt_fail(1, "pt_launch_metropolis_lighttracer: bad arguments (%d paths, %d rounds)", n_paths_per_light, mutation_rounds);
+        return nullptr;
+    }
+    PT_CUDA_NULL(cudaSetDevice(c->device), "select device");
+    const int ar = arith != PT_ARITH_SEPARATE ? PT_ARITH_FMA : PT_ARITH_SEPARATE;
+    const int nl = c->h_scene[ar]->nlights;
+    const int npaths = n_paths_per_light * nl;
+    if (ensure_vpls(c, 4 * npaths)) return nullptr;
+    const size_t need = (size_t)(npaths > 0 ? npaths : 1) * 80;
+    if (c->metro_cap < need) {
+        cudaFree(c->d_metro_seed); cudaFree(c->d_metro_mutated);
+        c->d_metro_seed = c->d_metro_mutated = nullptr;
+        c->metro_cap = 0;
+        PT_CUDA_NULL(cudaMalloc(&c->d_metro_seed, need), "alloc seed paths");
+        PT_CUDA_NULL(cudaMalloc(&c->d_metro_mutated, need), "alloc mutated paths");
+        c->metro_cap = need;
+    }
+    pt_camera cam0;
+    memset(&cam0, 0, sizeof(cam0));
+    pt_render_params rp0;
+    memset(&rp0, 0, sizeof(rp0));
+    rp0.variant = PT_VARIANT_LMEM; rp0.width = 1; rp0.height = 1; rp0.spp = 64; rp0.arith = ar;
+    memcpy(rp0.seeds, seeds, sizeof(rp0.seeds));
+    pt::LaunchArgs LA;
+    fill_args(c, &cam0, &rp0, nullptr, nullptr, nullptr, &LA);
+    pt_event e = event_new(c);
+    if (!e) return nullptr;
+    cudaEventRecord(e->start, c->stream);
+    DevLock lock(c->device);
+    if (pt_launch_metropolis_kernels(c, ar, LA, n_paths_per_light, mutation_rounds, c->d_vpls, c->d_metro_seed, c->d_metro_mutated,
+                                     c->d_vpl_active, c->d_vpl_count)) {
+        pt_release_event(e);
+        return nullptr;
+    }
+    cudaEventRecord(e->stop, c->stream);
+    c->nvpl = 4 * npaths;
+    c->n_metro_paths = npaths;
+    c->vlp_grid_set = false;          // a VLP grid built on the previous buffer is stale
+    c->vpls_set = true;
+    return e;
+}
+
+extern "C" int pt_read_metropolis_paths(pt_ctx c, uint32_t *paths, int capacity_paths, int mutated) {
+    if (!c) { pt_fail(1, "pt_read_metropolis_paths: null context"); return -1; }
+    if (!paths) return c->n_metro_paths;
+    if (capacity_paths < c->n_metro_paths) { pt_fail(1, "pt_read_metropolis_paths: buffer too small (%d < %d)", capacity_paths, c->n_metro_paths); return -1; }
+    if (cudaSetDevice(c->device) != cudaSuccess) { pt_fail(1, "select device"); return -1; }
+    if (c->n_metro_paths > 0 &&
+        (cudaMemcpyAsync(paths, mutated ? c->d_metro_mutated : c->d_metro_seed, (size_t)c->n_metro_paths * 80, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+         cudaStreamSynchronize(c->stream) != cudaSuccess)) {
+        pt_fail(1, "pt_read_metropolis_paths: copy failed");
+        return -1;
+    }
+    return c->n_metro_paths;
 }
 
 extern "C" int pt_set_vpls(pt_ctx c, const float *vpls, int n) {

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
         assert n in _lib.PTCUDA_SYMBOLS, "ctypes table misses %s" % n
     for n in declared_functions("pthost.h"):
         assert hasattr(host, n), "libpthost.so does not export %s" % n
-    assert cuda.pt_abi_version() == 4
+    assert cuda.pt_abi_version() == 5
 
 
 def test_struct_layouts_match_header(tmp_path):
