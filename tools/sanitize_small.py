@@ -30,6 +30,7 @@ with pt.Renderer(0) as r, tempfile.TemporaryDirectory() as tmp:
         if v == "bidir":
             r.light_tracer(S, 512); r.light_tracer(S, 33); r.read_vpls(); r.set_vpls(np.zeros((0, 4), np.float32)); r.light_tracer(S, 512)
         if v == "vlpgrid":
+            r.metropolis_light_tracer(S, 64, 2); r.read_metropolis_paths(mutated=True)
             r.light_tracer(S, 512)
             lo, hi = r.vlp_bounds()
             r.build_vlp_grid(pt.vlp_grid_dims(lo, hi, 1024, 3.0))
