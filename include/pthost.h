@@ -56,6 +56,8 @@ void pth_seeds(uint32_t seeds[4]);
 /* Complete drop-in program: argv, stdout lines, scene files from CWD and result.ppm as the reference
  * main() of the given PT_VARIANT_* (used by the four CLSuperPathTracer executables). */
 int pth_cli_main(int variant, int argc, char **argv);
+/* CLSuperMetropolisPathTracer_vlpgrid/CLSuperMetropolisPathTracer.c:429-720 (its kernels in FIX mode, ptcuda.h) */
+int pth_cli_metropolis_main(int argc, char **argv);
 
 #ifdef __cplusplus
 }

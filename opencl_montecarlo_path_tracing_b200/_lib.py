@@ -169,6 +169,7 @@ PTHOST_SYMBOLS = {
     "pth_save_png": (_I, [C.c_char_p, _I, _I, _VP]),
     "pth_import_obj": (C.c_long, [C.c_char_p, C.c_char_p, C.c_float, _FP]),
     "pth_cli_main": (_I, [_I, _I, C.POINTER(C.c_char_p)]),
+    "pth_cli_metropolis_main": (_I, [_I, C.POINTER(C.c_char_p)]),
 }
 
 _cuda = None

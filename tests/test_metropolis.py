@@ -13,6 +13,8 @@ work-item is (seeds.x ^ seeds.z, seeds.y ^ seeds.w) * 2^-32 — with the host's 
 rejects it, the "second" direction of Mutate equals the first, and Mutate changes no path at all (0 of 1792 probed); seeds
 outside that range (`extra*`) reach the other branches, and one set makes Mutate extend 11 of 512 paths."""
 import os
+import re
+import subprocess
 
 import numpy as np
 import pytest
@@ -120,3 +122,36 @@ def test_cuda_metropolis_vpls_feed_the_path_tracers(renderer, oracle_sep, scene_
     ref = oracle_sep.render("vlpgrid", 512, 512, SEED_SETS[0], osc, vpls=vpl, rows=rows)
     assert np.array_equal(res.accum[rows[0]:rows[1]].view(np.uint32), ref["accum"][rows[0]:rows[1]].view(np.uint32))
     assert np.array_equal(res.image[rows[0]:rows[1]], ref["image"][rows[0]:rows[1]])
+
+
+@pytest.mark.gpu
+def test_cli_metropolis_vlpgrid_dropin(scene_dirs, oracle_fma):
+    """bin/CLSuperMetropolisPathTracer_vlpgrid/CLSuperMetropolisPathTracer: the reference host's argv and stdout lines in its
+    order (CLSuperMetropolisPathTracer.c:429-720), result.ppm == the oracle's FIX-mode pipeline for the printed seeds."""
+    exe = os.path.join(ROOT, "opencl_montecarlo_path_tracing_b200", "bin", "CLSuperMetropolisPathTracer_vlpgrid", "CLSuperMetropolisPathTracer")
+    d = scene_dirs["bidir"]
+    env = dict(os.environ, PT_SEEDS="1,2,3,4")
+    W, H, n_paths, rounds, mod = 192, 128, 300, 5, 2.5
+    p = subprocess.run([exe, str(W), str(H), str(n_paths), str(rounds), str(mod)], cwd=d, env=env, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    out, pos = p.stdout, 0
+    for token in ["Usage:", "[N_seedpaths_per_light] [mutation_rounds] [CELL_SIZE_MODIFIER]", "number of platforms:", "selected device", "Seeds: 1, 2, 3, 4",
+                  "Processing image 192x128 with data size 98304 bytes", "Cam values:", "Number of triangles:", "Number of lights: 2",
+                  "Mutation rounds: 5", "gws: 2560, lws: 256", "gws: 256, lws: 256", "VLPs bounding box values:", "VLPs grid size:",
+                  "Successfully created render image result.ppm", "light paths random sampling : 600 random light paths",
+                  "light paths metropolis sampling : 2400 virtual lights", "VLPs min/max reduction", "Read VLPs bounding box", "init VLPs grid :",
+                  "rendering : 24576 pixels", "read render data : 98304 uchar", "Total time:"]:
+        k = out.find(token, pos)
+        assert k >= 0, "stdout misses %r after offset %d:\n%s" % (token, pos, out)
+        pos = k
+    osc = oracle_fma.load_scene_dir(d, "bidir")
+    _, vpl = oracle_fma.metropolis_light_tracer((1, 2, 3, 4), osc, n_paths, rounds)
+    ref = oracle_fma.render("vlpgrid", W, H, (1, 2, 3, 4), osc, vpls=vpl, modifier=mod, want_accum=False, want_rng=False)
+    g = ref["vlp_grid"]
+    m = re.search(r"VLPs grid size: (\d+) x (\d+) x (\d+)", out)
+    assert [int(x) for x in m.groups()] == [int(x) for x in g["res"][:3]]
+    lo, hi = oracle_fma.vlp_bounds(vpl)
+    assert ("vmax: %f %f %f, vmin: %f %f %f" % (hi[0], hi[1], hi[2], lo[0], lo[1], lo[2])) in out
+    tmp = os.path.join(d, "oracle_expected_metro.ppm")
+    oracle_fma.save_pam(tmp, ref["image"])
+    assert open(os.path.join(d, "result.ppm"), "rb").read() == open(tmp, "rb").read()
