@@ -771,6 +771,13 @@ def bench_ours(args, wname, default_workload):
                 if sub.get("parity_check") and sub["parity_check"].get("bit_exact") is False:
                     ok = False
             line["configs"] = extras
+            if DEFAULT_MULTI in extras:
+                # the N > 1 default strong-scales ANOTHER workload (BASELINE config 5) than this line's headline (config 4):
+                # its one-GPU point, for whoever computes a scaling efficiency from the per-N lines
+                e = extras[DEFAULT_MULTI]
+                line["strong_scaling_n1"] = {"workload": DEFAULT_MULTI, "value": e["value"], "unit": e["unit"], "ms_per_step": e["ms_per_step"],
+                                             "e2e": e.get("e2e"), "note": "bench.py --gpus N (N > 1) measures this workload; divide its "
+                                             "value by N x this one for the strong-scaling efficiency"}
             sct = simple_cpu_tracer_baseline()
             if sct:
                 line["simple_cpu_tracer"] = sct
