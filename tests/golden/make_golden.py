@@ -259,6 +259,18 @@ def bidir_golden(tmp):
     np.savez_compressed(os.path.join(HERE, "golden_bidir.npz"), **out)
 
 
+def canonical_paths(paths):
+    """The reference's Path records carry stack garbage in everything that is not defined — vertices at and beyond `length`, the
+    w components, the padding after `length`: zero it, so that the golden file is a function of the program alone."""
+    p = np.array(paths, np.uint32).reshape(-1, 20).copy()
+    for i in range(p.shape[0]):
+        n = min(int(p[i, 16]), 4)
+        p[i, 4 * n:16] = 0
+        p[i, 3:16:4] = 0
+        p[i, 17:] = 0
+    return p
+
+
 def ref_metropolis_vpls(L, sc, seeds, n_paths, rounds):
     """FIX build of the reference (oracle/Makefile: `float t = 1e9;` in VerifyIntersection, nothing else): kernel lightTracer
     writes the seed paths into ITS OWN buffer (the reference host hands it d_virtual_lights by mistake,
@@ -286,7 +298,7 @@ def ref_metropolis_vpls(L, sc, seeds, n_paths, rounds):
     gws = (C.c_size_t * 1)(n_paths)
     assert L.clEnqueueNDRangeKernel(None, k, 1, None, gws, None, 0, None, None) == 0
     ptr = L.clEnqueueMapBuffer(None, bp, 1, 1, C.c_size_t(0), C.c_size_t(paths.nbytes), 0, None, None, C.byref(err))
-    paths_out = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint32)), shape=paths.shape).copy()
+    paths_out = canonical_paths(np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint32)), shape=paths.shape))
     k2 = C.c_void_p(L.clCreateKernel(None, b"MetropolisLightTracer", C.byref(err)))
     args = [(8, C.byref(bs)), (8, C.byref(bq)), (8, C.byref(bt)), (4, C.byref(ntri)), (8, C.byref(bl)), (4, C.byref(nlc)),
             (8, C.byref(bp)), (8, C.byref(bv)), (16, sd), (4, C.byref(rd)), (36, None), (36, None), (16 * nl, None)]
@@ -340,7 +352,7 @@ def metropolis_golden(tmp):
                 mut[r].append(p)
     out["mutate_which"] = np.array(which, np.int32)
     for r in mut:
-        out["mutate_r%d" % r] = np.array(mut[r], np.uint32)
+        out["mutate_r%d" % r] = canonical_paths(mut[r])
     # The first RNG pair of EVERY work-item is (seeds.x ^ seeds.z, seeds.y ^ seeds.w) * 2^-32 (the seeding XORs one hash into all
     # four words), and Mutate branches on it: with the host's 27-bit seeds it is always < 0.03125, so `y > 0.3 / 0.7 / 0.9` and
     # `probability < x` never fire.  Seeds outside that range reach the other branches (the kernels take any uint4).
@@ -356,7 +368,7 @@ def metropolis_golden(tmp):
                                    tris.ctypes.data_as(C.c_void_p), C.c_int(tris.shape[0]), (C.c_float * 3)(*lights[l, :3]),
                                    p.ctypes.data_as(C.c_void_p), C.c_int(8))
                 res.append(p)
-        out["extra%d_mutated" % ei] = np.array(res, np.uint32)
+        out["extra%d_mutated" % ei] = canonical_paths(res)
     out["extra_seeds"] = np.array(METRO_EXTRA_SEEDS, np.uint32)
     if env_seeds is not None:
         os.environ["PT_SEEDS"] = env_seeds
@@ -451,7 +463,15 @@ def vlpgrid_golden(tmp):
         v4 = (C.c_float * 4)(*vmin); r4 = (C.c_int32 * 4)(*[int(x) for x in res]); c4 = (C.c_float * 4)(*cell)
         L.clSetKernelArg(kg, 0, C.c_size_t(8), C.byref(bc)); L.clSetKernelArg(kg, 1, C.c_size_t(8), C.byref(b1))
         L.clSetKernelArg(kg, 2, C.c_size_t(16), v4); L.clSetKernelArg(kg, 3, C.c_size_t(16), r4); L.clSetKernelArg(kg, 4, C.c_size_t(16), c4)
+        # a cell that overflows stores whichever 62 lights ARRIVE first (atomic_inc): a race between work-items.  Run this one
+        # kernel with the work-items in sequential order (one OpenMP thread), so that the stored set — the 62 lowest indices —
+        # is a function of the program and the file regenerates bit for bit.
+        gomp = C.CDLL("libgomp.so.1")
+        gomp.omp_get_max_threads.restype = C.c_int
+        nthreads = gomp.omp_get_max_threads()
+        gomp.omp_set_num_threads(1)
         assert L.clEnqueueNDRangeKernel(None, kg, 1, None, (C.c_size_t * 1)(n), None, 0, None, None) == 0
+        gomp.omp_set_num_threads(nthreads)
         ptr = L.clEnqueueMapBuffer(None, bc, 1, 1, C.c_size_t(0), C.c_size_t(cells.nbytes), 0, None, None, C.byref(err))
         got = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(ncells, 128)).copy()
         nels = got[:, :4].copy().view(np.uint32).reshape(-1)
